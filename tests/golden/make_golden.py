@@ -1,0 +1,175 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference.
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+It imports ``segment_anything`` from /root/reference/wildlifemapper, loads the deterministic
+synthetic weights from ``oracle/weights.py`` into the reference modules, runs the reference forward /
+PostProcess / torchvision NMS on seeded inputs and stores small fixtures:
+
+  golden_model_<cfg>.npz  logits, boxes, and per-stage samples (fixed pseudo-random positions)
+  golden_post.npz         PostProcess outputs for seeded logits/boxes
+  golden_nms.npz          torchvision.ops.nms keep lists (class-agnostic and per-class)
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference/wildlifemapper"
+
+from oracle import post as opost  # noqa: E402
+from oracle.weights import MODEL_CONFIGS, make_state_dict, make_tiles  # noqa: E402
+
+N_SAMPLES = 256
+
+
+def sample_positions(numel: int, key: str) -> np.ndarray:
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(key.encode()))
+    return rng.integers(0, numel, N_SAMPLES)
+
+
+def tap_summary(name: str, t: torch.Tensor) -> dict:
+    f = t.detach().float().contiguous().view(-1)
+    pos = sample_positions(f.numel(), name)
+    return {f"{name}.samples": f[torch.from_numpy(pos)].numpy(),
+            f"{name}.stats": np.array([f.mean().item(), f.abs().mean().item(), f.abs().max().item()], np.float64)}
+
+
+def build_reference(model_type: str, num_queries: int):
+    sys.path.insert(0, REF)
+    from segment_anything.modeling import ImageEncoderViT, MaskDecoder, PromptEncoder, TwoWayTransformer
+    from segment_anything.network import MedSAM
+    from functools import partial
+    D, depth, heads, glob = MODEL_CONFIGS[model_type]
+    enc = ImageEncoderViT(depth=depth, embed_dim=D, img_size=1024, mlp_ratio=4,
+                          norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_heads=heads, patch_size=16,
+                          qkv_bias=True, use_rel_pos=True, global_attn_indexes=list(glob), window_size=14,
+                          out_chans=256)
+    pe = PromptEncoder(embed_dim=256, image_embedding_size=(64, 64), input_image_size=(1024, 1024), mask_in_chans=16)
+    dec = MaskDecoder(num_multimask_outputs=num_queries - 1,
+                      transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
+                      transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256)
+    model = MedSAM(image_encoder=enc, mask_decoder=dec, prompt_encoder=pe).eval()
+    return model
+
+
+def golden_model(model_type: str, batch: int, num_queries: int, tag: str) -> None:
+    sd = make_state_dict(model_type, seed=0, num_queries=num_queries)
+    model = build_reference(model_type, num_queries)
+    ref_keys = list(model.state_dict().keys())
+    assert ref_keys == list(sd.keys()), "state_dict key contract drifted"
+    for k, v in model.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    model.load_state_dict(sd, strict=True)
+    from segment_anything.utils.misc import NestedTensor
+    tiles = make_tiles(batch, seed=2)
+    taps = {}
+
+    def hook(name):
+        def fn(_m, _i, o):
+            taps[name] = o
+        return fn
+
+    enc = model.image_encoder
+    enc.patch_embed.register_forward_hook(hook("patch"))
+    enc.hfc_embed.register_forward_hook(hook("hfc_tok"))
+    enc.hfc_attn.register_forward_hook(hook("hfc_attn_out"))
+    for i, blk in enumerate(enc.blocks):
+        blk.register_forward_hook(hook(f"block{i}"))
+    enc.register_forward_hook(hook("features"))
+    model.mask_decoder.transformer.register_forward_hook(hook("transformer"))
+    with torch.no_grad():
+        x_hfc = model.fft(NestedTensor(tiles, None))
+        out = model(NestedTensor(tiles, None), np.array([[0, 0, 1024, 1024]] * batch))
+    res = {"pred_logits": out["pred_logits"].numpy(), "pred_boxes": out["pred_boxes"].numpy()}
+    res.update(tap_summary("x_hfc", x_hfc))
+    for k, v in taps.items():
+        if k == "transformer":
+            res.update(tap_summary("hs", v[0]))
+        else:
+            res.update(tap_summary(k, v))
+    # reference PostProcess on the reference outputs
+    sys.path.insert(0, REF)
+    from segment_anything.build_sam import PostProcess
+    ts = torch.tensor([[1024, 1024]] * batch)
+    pp = PostProcess(0.05)(out, ts)
+    for i, r in enumerate(pp):
+        res[f"pp{i}.scores"] = r["scores"].numpy()
+        res[f"pp{i}.labels"] = r["labels"].numpy()
+        res[f"pp{i}.boxes"] = r["boxes"].numpy()
+    res["meta"] = np.array([batch, num_queries])
+    np.savez_compressed(os.path.join(HERE, f"golden_model_{tag}.npz"), **res)
+    print("wrote", tag, {k: v.shape for k, v in res.items() if not k.endswith(("samples", "stats"))})
+
+
+def golden_post() -> None:
+    sys.path.insert(0, REF)
+    from segment_anything.build_sam import PostProcess
+    g = torch.Generator().manual_seed(11)
+    res = {}
+    for case, (B, Q, spread) in enumerate(((3, 51, 2.0), (2, 900, 4.0), (2, 51, 0.01))):
+        logits = torch.randn(B, Q, 8, generator=g) * spread
+        if case == 2:
+            logits[..., -1] += 8.0  # everything below threshold in image 0 -> empty result branch
+            logits[1, 5, 2] += 12.0
+        boxes = torch.rand(B, Q, 4, generator=g) * 0.5 + 0.1
+        ts = torch.tensor([[1024, 1024], [768, 1000], [3648, 5472]][:B])
+        out = PostProcess(0.05)({"pred_logits": logits, "pred_boxes": boxes}, ts)
+        res[f"c{case}.logits"] = logits.numpy()
+        res[f"c{case}.boxes"] = boxes.numpy()
+        res[f"c{case}.sizes"] = ts.numpy()
+        for i, r in enumerate(out):
+            res[f"c{case}.{i}.scores"] = r["scores"].numpy().astype(np.float32)
+            res[f"c{case}.{i}.labels"] = r["labels"].numpy().astype(np.int64)
+            res[f"c{case}.{i}.boxes"] = r["boxes"].numpy().astype(np.float32).reshape(-1, 4)
+    np.savez_compressed(os.path.join(HERE, "golden_post.npz"), **res)
+    print("wrote golden_post")
+
+
+def golden_nms() -> None:
+    import torchvision
+    res = {"torchvision": np.array(torchvision.__version__)}
+    for tag, n, dup in (("n2000", 2000, False), ("n2000dup", 2000, True), ("n10000", 10000, False)):
+        b, s, l = opost.make_nms_problem(n, seed=3, dup_scores=dup)
+        tb, ts_ = torch.from_numpy(b), torch.from_numpy(s)
+        keep = torchvision.ops.nms(tb, ts_, 0.4).numpy()
+        kc = []
+        for c in range(7):  # per-class loop == _batched_nms_vanilla semantics
+            idx = np.nonzero(l == c)[0]
+            kc.append(idx[torchvision.ops.nms(tb[idx], ts_[idx], 0.4).numpy()])
+        kc = np.sort(np.concatenate(kc))  # ties: lower original index first (as _batched_nms_vanilla's where())
+        kc = kc[np.argsort(-s[kc], kind="stable")]
+        res[f"{tag}.keep"] = keep.astype(np.int32)
+        res[f"{tag}.keep_per_class"] = kc.astype(np.int32)
+    # exact-tie probes: IoU == 2/5 vs threshold 0.4 in double
+    tie_boxes = np.array([[0, 0, 10, 10], [0, 0, 10, 4], [0, 0, 4, 10], [20, 20, 30, 30], [20, 20, 30, 24]], np.float32)
+    tie_scores = np.array([0.9, 0.8, 0.7, 0.7, 0.7], np.float32)
+    res["tie.boxes"], res["tie.scores"] = tie_boxes, tie_scores
+    res["tie.keep"] = torchvision.ops.nms(torch.from_numpy(tie_boxes), torch.from_numpy(tie_scores), 0.4).numpy().astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "golden_nms.npz"), **res)
+    print("wrote golden_nms", {k: (v.shape if hasattr(v, "shape") else v) for k, v in res.items()})
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count() or 8)
+    which = sys.argv[1:] or ["post", "nms", "vit_t", "vit_t900", "vit_b"]
+    if "post" in which:
+        golden_post()
+    if "nms" in which:
+        golden_nms()
+    if "vit_t" in which:
+        golden_model("vit_t", 2, 51, "vit_t")
+    if "vit_t900" in which:
+        golden_model("vit_t", 1, 900, "vit_t_q900")
+    if "vit_b" in which:
+        golden_model("vit_b", 1, 51, "vit_b")

@@ -1,0 +1,312 @@
+"""Kernel-level parity tests on the B200: every C-ABI entry point against a plain fp32 torch / numpy restatement
+of the same op on the same seeded inputs.  Integer outputs must be bit-exact; float tolerances are stated inline."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # collected on CPU boxes too; -m gpu selects them only on the GPU box
+    pytest.skip("needs a GPU", allow_module_level=True)
+
+from wildlifemapper_b200.ops import ops  # noqa: E402
+from oracle import post as opost  # noqa: E402
+
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def rel_err(got, ref):
+    return ((got.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-6)).item()
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 256, 64, 0), (256, 256, 128, 0), (1000, 768, 768, 0), (4096, 2304, 768, 0), (4096, 768, 3072, 0),
+    (384, 128, 256, 0), (51, 8, 256, 0), (300, 4, 256, 0), (1632, 2048, 256, 0), (1632, 256, 2048, 0),
+    (512, 1024, 1024, 128), (512, 1280, 1280, 0), (640, 192, 128, 64), (20000, 256, 768, 0),
+])
+def test_gemm_matches_fp32(M, N, K, bn):
+    a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
+    out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(a, w, None, None, 0, None, out, 0, bn)
+    ref = a.float() @ w.float().t()
+    assert rel_err(out, ref) < 2e-3  # bf16 products are exact in fp32; only accumulation order differs
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_gemm_epilogues(act):
+    M, N, K = 700, 768, 256
+    a, w = rnd(M, K, seed=3), rnd(N, K, seed=4, scale=K ** -0.5)
+    bias = rnd(N, seed=5, dtype=torch.float32)
+    res = rnd(100, N, seed=6, dtype=torch.float32)
+    o32 = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    o16 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, bias, res, 100, o16, o32, act, 0)
+    y = a.float() @ w.float().t() + bias
+    y = [y, torch.nn.functional.gelu(y), torch.relu(y), torch.sigmoid(y)][act]
+    y = y + res[torch.arange(M, device=DEV) % 100]
+    assert (o32 - y).abs().max().item() < 5e-3
+    assert (o16.float() - y).abs().max().item() < 5e-2  # bf16 rounding of values up to ~6
+
+
+def test_gemm_strided_views():
+    # A and the outputs are column slices of wider buffers (how qkv / kv projections are consumed)
+    M, N, K = 512, 256, 128
+    big = rnd(M, 3 * K, seed=7)
+    a = big[:, K:2 * K]
+    w = rnd(N, K, seed=8, scale=K ** -0.5)
+    outbig = torch.zeros(M, 2 * N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, None, None, 0, outbig[:, N:], None, 0, 0)
+    ref = a.float() @ w.float().t()
+    assert rel_err(outbig[:, N:], ref) < 1e-2
+    assert outbig[:, :N].abs().max().item() == 0
+
+
+def test_conv3x3_matches_conv2d():
+    B, C, N = 2, 256, 256
+    x = rnd(B, 64, 64, C, seed=9)
+    wt = rnd(N, C, 3, 3, seed=10, scale=(9 * C) ** -0.5)
+    w2 = wt.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = torch.empty(B * 4096, N, device=DEV, dtype=torch.float32)
+    ops.conv3x3(x, w2, None, out)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1)
+    assert rel_err(out.view(B, 64, 64, N), ref) < 2e-3
+
+
+# ------------------------------------------------------------------ bandwidth kernels
+@pytest.mark.parametrize("D", [128, 256, 768, 1024, 1280])
+def test_layernorm(D):
+    rows = 1000
+    x = rnd(rows, D, seed=11, scale=3.0, dtype=torch.float32) + 0.5
+    g, b = rnd(D, seed=12, dtype=torch.float32), rnd(D, seed=13, dtype=torch.float32)
+    add = rnd(64, D, seed=14, dtype=torch.float32)
+    y16 = torch.empty(rows, D, device=DEV, dtype=torch.bfloat16)
+    y32 = torch.empty(rows, D, device=DEV, dtype=torch.float32)
+    y2 = torch.empty(rows, D, device=DEV, dtype=torch.bfloat16)
+    ops.layernorm(x, g, b, y16, y32, add, 64, y2, 1e-6)
+    ref = torch.nn.functional.layer_norm(x, (D,), g, b, 1e-6)
+    assert (y32 - ref).abs().max().item() < 2e-5
+    assert (y16.float() - ref).abs().max().item() <= ref.abs().max().item() * 2 ** -8
+    ref2 = ref + add[torch.arange(rows, device=DEV) % 64]
+    assert (y2.float() - ref2).abs().max().item() <= ref2.abs().max().item() * 2 ** -8
+
+
+def test_patchify_and_gray():
+    B = 2
+    img = rnd(B, 3, 1024, 1024, seed=15, dtype=torch.float32)
+    patches = torch.empty(B * 4096, 768, device=DEV, dtype=torch.bfloat16)
+    gray = torch.empty(B, 1024, 1024, device=DEV, dtype=torch.bfloat16)
+    ops.patchify(img, patches, gray)
+    ref = torch.nn.functional.unfold(img, 16, stride=16).transpose(1, 2).reshape(B * 4096, 768)  # (c,ky,kx) order
+    assert torch.equal(patches, ref.to(torch.bfloat16))
+    g = 0.2989 * img[:, 0] + 0.587 * img[:, 1] + 0.114 * img[:, 2]
+    assert (gray.float() - g).abs().max().item() < 0.02
+
+
+@pytest.mark.parametrize("R,C,dt", [(1024, 4096, torch.bfloat16), (4096, 256, torch.float32), (100, 70, torch.float32)])
+def test_transpose(R, C, dt):
+    x = rnd(3, R, C, seed=16, dtype=dt)
+    out = torch.empty(3, C, R, device=DEV, dtype=dt)
+    ops.transpose(x, out)
+    assert torch.equal(out, x.transpose(1, 2).contiguous())
+
+
+def test_hfc_finalize():
+    B = 2
+    img = rnd(B, 3, 1024, 1024, seed=17, dtype=torch.float32)
+    low = rnd(B, 1024, 1024, seed=18, dtype=torch.float32)  # low[b][y][x]
+    low_t = low.transpose(1, 2).contiguous()
+    patches = torch.empty(B * 4096, 256, device=DEV, dtype=torch.bfloat16)
+    himg = torch.empty(B, 1024, 1024, device=DEV, dtype=torch.float32)
+    ops.hfc_finalize(img, low_t, patches, himg)
+    g = 0.2989 * img[:, 0] + 0.587 * img[:, 1] + 0.114 * img[:, 2]
+    ref = (g - low).abs()
+    assert (himg - ref).abs().max().item() < 1e-5
+    refp = torch.nn.functional.unfold(ref[:, None], 16, stride=16).transpose(1, 2).reshape(B * 4096, 256)
+    assert (patches.float() - refp).abs().max().item() <= refp.abs().max().item() * 2 ** -8
+
+
+def test_add_cast():
+    a = rnd(500, 256, seed=19, dtype=torch.float32)
+    b = rnd(50, 256, seed=20, dtype=torch.float32)
+    out = torch.empty(500, 256, device=DEV, dtype=torch.bfloat16)
+    ops.add_cast(a, b, 50, out)
+    assert torch.equal(out, (a + b[torch.arange(500, device=DEV) % 50]).to(torch.bfloat16))
+    ops.add_cast(a, None, 0, out)
+    assert torch.equal(out, a.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------ attention
+def ref_attention(q, k, v, scale, bias=None):
+    s = (q.float() * scale) @ k.float().transpose(-1, -2)
+    if bias is not None:
+        s = s + bias
+    return torch.softmax(s, -1) @ v.float()
+
+
+@pytest.mark.parametrize("Tq,Tk,hd,H", [(51, 51, 32, 8), (51, 4096, 16, 8), (4096, 51, 16, 8), (900, 900, 32, 8), (7, 130, 16, 2)])
+def test_attn_small(Tq, Tk, hd, H):
+    B = 2
+    q, k, v = rnd(B * Tq, H * hd, seed=21), rnd(B * Tk, H * hd, seed=22), rnd(B * Tk, H * hd, seed=23)
+    out = torch.empty(B * Tq, H * hd, device=DEV, dtype=torch.bfloat16)
+    scale = 1 / math.sqrt(hd)
+    ops.attn_small(q, k, v, out, B, H, Tq, Tk, hd, scale)
+    sp = lambda t, T: t.view(B, T, H, hd).transpose(1, 2)
+    ref = ref_attention(sp(q, Tq), sp(k, Tk), sp(v, Tk), scale).transpose(1, 2).reshape(B * Tq, H * hd)
+    assert (out.float() - ref).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("hd,H,T", [(64, 2, 256), (64, 3, 4096), (128, 2, 512), (128, 8, 4096)])
+def test_attn_flash_plain(hd, H, T):
+    B = 2 if T <= 512 else 1
+    q = rnd(B * T, H * hd, seed=24)
+    kv = rnd(B * T, 2 * H * hd, seed=25)
+    out = torch.zeros(B * T, H * hd, device=DEV, dtype=torch.bfloat16)
+    scale = 1 / math.sqrt(hd)
+    ops.attn_flash(q, 0, kv, 0, kv, H * hd, None, out, B, H, T, T, hd, scale)
+    sp = lambda t: t.reshape(B, T, H, hd).transpose(1, 2)
+    ref = ref_attention(sp(q), sp(kv[:, :H * hd]), sp(kv[:, H * hd:]), scale).transpose(1, 2).reshape(B * T, H * hd)
+    # P is rounded to bf16 before the P.V MMA and the output to bf16: ~2^-8 relative
+    assert (out.float() - ref).abs().max().item() < 2e-2
+
+
+def relpos_bias(q, rel_h, rel_w, S):
+    """q [B,H,S*S,hd] (unscaled) -> bias [B,H,S*S,S*S]; image_encoder.py:347-383."""
+    idx = (torch.arange(S)[:, None] - torch.arange(S)[None, :] + S - 1).to(q.device)
+    Rh, Rw = rel_h.float()[idx], rel_w.float()[idx]
+    B, H, T, hd = q.shape
+    rq = q.float().view(B, H, S, S, hd)
+    bh = torch.einsum("bnhwc,hkc->bnhwk", rq, Rh)
+    bw = torch.einsum("bnhwc,wkc->bnhwk", rq, Rw)
+    return (bh[..., :, None] + bw[..., None, :]).reshape(B, H, T, T)
+
+
+def test_attn_flash_global_relpos():
+    B, H, hd, T = 1, 2, 64, 4096
+    D = H * hd
+    qkv = rnd(B * T, 3 * D, seed=26)
+    rel_h, rel_w = rnd(127, hd, seed=27, scale=0.3), rnd(127, hd, seed=28, scale=0.3)
+    table = torch.zeros(256, 64, device=DEV, dtype=torch.bfloat16)
+    table[:127], table[128:255] = rel_h, rel_w
+    out = torch.zeros(B * T, D, device=DEV, dtype=torch.bfloat16)
+    scale = hd ** -0.5
+    ops.attn_flash(qkv, 0, qkv, D, qkv, 2 * D, table, out, B, H, T, T, hd, scale)
+    sp = lambda t: t.reshape(B, T, H, hd).transpose(1, 2)
+    q, k, v = sp(qkv[:, :D]), sp(qkv[:, D:2 * D]), sp(qkv[:, 2 * D:])
+    ref = ref_attention(q, k, v, scale, relpos_bias(q, rel_h, rel_w, 64)).transpose(1, 2).reshape(B * T, D)
+    assert (out.float() - ref).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,H", [(1, 2), (2, 12)])
+def test_attn_window(B, H):
+    hd, S = 64, 14
+    D = H * hd
+    qkv = rnd(B, 64, 64, 3 * D, seed=29)
+    rel_h, rel_w = rnd(27, hd, seed=30, scale=0.3), rnd(27, hd, seed=31, scale=0.3)
+    table = torch.zeros(64, 64, device=DEV, dtype=torch.bfloat16)
+    table[:27], table[32:59] = rel_h, rel_w
+    out = torch.zeros(B, 64, 64, D, device=DEV, dtype=torch.bfloat16)
+    scale = hd ** -0.5
+    ops.attn_window(qkv, table, out, H, scale)
+    # reference: zero-pad the (bias-free) qkv to 70x70 -> pad tokens are exact zero keys/values that still
+    # take part in the softmax with their rel-pos bias
+    xp = torch.nn.functional.pad(qkv.float(), (0, 0, 0, 6, 0, 6))
+    win = xp.view(B, 5, S, 5, S, 3 * D).permute(0, 1, 3, 2, 4, 5).reshape(B * 25, S * S, 3, H, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = win[0], win[1], win[2]
+    o = ref_attention(q, k, v, scale, relpos_bias(q, rel_h, rel_w, S))  # [B*25,H,196,hd]
+    o = o.transpose(1, 2).reshape(B, 5, 5, S, S, D).permute(0, 1, 3, 2, 4, 5).reshape(B, 70, 70, D)[:, :64, :64]
+    assert (out.float() - o).abs().max().item() < 2e-2
+
+
+# ------------------------------------------------------------------ post-process (integer stages bit-exact)
+def test_postprocess_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "golden_post.npz"))
+    for case in range(3):
+        logits = torch.from_numpy(g[f"c{case}.logits"]).to(DEV)
+        boxes = torch.from_numpy(g[f"c{case}.boxes"]).to(DEV)
+        sizes = torch.from_numpy(g[f"c{case}.sizes"]).to(DEV)
+        B, Q, _ = logits.shape
+        packed = torch.zeros(B, Q, 6, device=DEV)
+        qidx = torch.zeros(B, Q, device=DEV, dtype=torch.int32)
+        counts = torch.zeros(B, device=DEV, dtype=torch.int32)
+        ops.postprocess(logits, boxes, sizes, 0.05, 0, packed, qidx, counts)
+        for i in range(B):
+            n = int(counts[i])
+            ref_l = g[f"c{case}.{i}.labels"]
+            assert n == ref_l.shape[0]
+            np.testing.assert_array_equal(packed[i, :n, 5].cpu().numpy().astype(np.int64), ref_l)
+            np.testing.assert_allclose(packed[i, :n, 4].cpu().numpy(), g[f"c{case}.{i}.scores"], atol=5e-7, rtol=0)
+            np.testing.assert_allclose(packed[i, :n, :4].cpu().numpy(), g[f"c{case}.{i}.boxes"], atol=1e-3, rtol=0)
+        # integer stage fed the oracle's probabilities: labels, keep set and boxes bit-exact
+        prob = opost.softmax_f32(g[f"c{case}.logits"])
+        ref = opost.select_from_prob(prob, g[f"c{case}.boxes"], g[f"c{case}.sizes"], 0.05)
+        ops.postprocess(torch.from_numpy(prob).to(DEV), boxes, sizes, 0.05, 1, packed, qidx, counts)
+        for i in range(B):
+            n = int(counts[i])
+            assert n == ref[i]["labels"].shape[0]
+            np.testing.assert_array_equal(qidx[i, :n].cpu().numpy(), ref[i]["query"])
+            np.testing.assert_array_equal(packed[i, :n, 5].cpu().numpy().astype(np.int64), ref[i]["labels"])
+            np.testing.assert_array_equal(packed[i, :n, 4].cpu().numpy(), ref[i]["scores"])
+            np.testing.assert_array_equal(packed[i, :n, :4].cpu().numpy(), ref[i]["boxes"])
+
+
+def test_sigmoid_topk_bit_exact():
+    B, Q, K = 2, 900, 300
+    rng = np.random.default_rng(5)
+    logits = (rng.standard_normal((B, Q, 8)) * 2).astype(np.float32)
+    logits = np.round(logits * 4) / 4  # many exact ties
+    boxes = rng.random((B, Q, 4)).astype(np.float32)
+    prob = opost.sigmoid_f32(logits[..., :7]).reshape(B, Q * 7)
+    ref_s, ref_idx = opost.topk_from_prob(prob, K)
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    prob_ws, order_ws = t(prob.copy()), torch.zeros(B, Q * 7, device=DEV, dtype=torch.int32)
+    scores, labels = torch.zeros(B, K, device=DEV), torch.zeros(B, K, device=DEV, dtype=torch.int32)
+    query, ob = torch.zeros(B, K, device=DEV, dtype=torch.int32), torch.zeros(B, K, 4, device=DEV)
+    ops.sigmoid_topk(t(logits), t(boxes), prob_ws, order_ws, scores, labels, query, ob, 7, K, 1)
+    np.testing.assert_array_equal(scores.cpu().numpy(), ref_s)
+    np.testing.assert_array_equal(labels.cpu().numpy(), ref_idx % 7)
+    np.testing.assert_array_equal(query.cpu().numpy(), ref_idx // 7)
+    np.testing.assert_array_equal(ob.cpu().numpy(), np.take_along_axis(boxes, (ref_idx // 7)[..., None], 1))
+    # float stage (own sigmoid): same selection up to fp32 rounding of the scores
+    ops.sigmoid_topk(t(logits), t(boxes), prob_ws, order_ws, scores, labels, query, ob, 7, K, 0)
+    np.testing.assert_allclose(scores.cpu().numpy(), ref_s, atol=2e-7, rtol=0)
+
+
+def _run_nms(b, s, l, thr=0.4):
+    n = b.shape[0]
+    nb = (n + 63) // 64
+    keep = torch.zeros(max(n, 1), device=DEV, dtype=torch.int64)
+    num = torch.zeros(1, device=DEV, dtype=torch.int32)
+    ops.nms(torch.from_numpy(b).to(DEV).reshape(-1, 4), torch.from_numpy(s).to(DEV),
+            None if l is None else torch.from_numpy(l).to(DEV), thr,
+            torch.zeros(max(n, 1), device=DEV, dtype=torch.int32), torch.zeros(max(n * nb, 1), device=DEV, dtype=torch.int64),
+            keep, num)
+    return keep[:int(num)].cpu().numpy()
+
+
+@pytest.mark.parametrize("tag,n,dup", [("n2000", 2000, False), ("n2000dup", 2000, True), ("n10000", 10000, False)])
+def test_nms_golden_bit_exact(golden_dir, tag, n, dup):
+    g = np.load(os.path.join(golden_dir, "golden_nms.npz"))
+    b, s, l = opost.make_nms_problem(n, seed=3, dup_scores=dup)
+    np.testing.assert_array_equal(_run_nms(b, s, None), g[f"{tag}.keep"].astype(np.int64))
+    np.testing.assert_array_equal(_run_nms(b, s, l), g[f"{tag}.keep_per_class"].astype(np.int64))
+
+
+def test_nms_edges(golden_dir):
+    g = np.load(os.path.join(golden_dir, "golden_nms.npz"))
+    np.testing.assert_array_equal(_run_nms(g["tie.boxes"], g["tie.scores"], None), g["tie.keep"].astype(np.int64))
+    assert _run_nms(np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), None).shape == (0,)
+    z = np.array([[5, 5, 5, 5], [5, 5, 5, 5]], np.float32)
+    np.testing.assert_array_equal(_run_nms(z, np.array([0.9, 0.8], np.float32), None), [0, 1])
+    for seed in range(3):
+        b, s, l = opost.make_nms_problem(777, seed=seed, dup_scores=bool(seed % 2))
+        np.testing.assert_array_equal(_run_nms(b, s, None), opost.nms(b, s, 0.4))
+        np.testing.assert_array_equal(_run_nms(b, s, l), opost.batched_nms(b, s, l, 0.4))

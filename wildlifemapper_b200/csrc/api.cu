@@ -1,0 +1,318 @@
+// C ABI (include/wm_b200.h): argument validation, TMA tensor-map construction, dispatch.  No torch types.
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+#include "../../include/wm_b200.h"
+#include "wm_internal.h"
+
+namespace wm {
+int layernorm_launch(const float*, const float*, const float*, __nv_bfloat16*, float*, const float*, int,
+                     __nv_bfloat16*, int, int, float, cudaStream_t);
+int patchify_launch(const float*, __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t);
+int transpose_launch(const void*, void*, int, int, int, int, cudaStream_t);
+int hfc_finalize_launch(const float*, const float*, __nv_bfloat16*, float*, int, cudaStream_t);
+int add_cast_launch(const float*, const float*, int, __nv_bfloat16*, int, int, cudaStream_t);
+int attn_small_launch(const __nv_bfloat16*, int, const __nv_bfloat16*, int, const __nv_bfloat16*, int, __nv_bfloat16*,
+                      int, int, int, int, int, int, float, cudaStream_t);
+int postprocess_launch(const float*, const float*, const long long*, float, int, float*, int*, int*, int, int, int,
+                       cudaStream_t);
+int sigmoid_topk_launch(const float*, const float*, float*, int*, float*, int*, int*, float*, int, int, int, int, int,
+                        int, cudaStream_t);
+int nms_launch(const float*, const float*, const long long*, int, double, int*, unsigned long long*, long long*, int*,
+               cudaStream_t);
+}  // namespace wm
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+int check_launch(int rc, const char* what) {
+  if (rc == WM_OK) return WM_OK;
+  if (rc == WM_ERR_CUDA) return fail(rc, "%s: CUDA error: %s", what, cudaGetErrorString(cudaGetLastError()));
+  return fail(rc, "%s: unsupported shape", what);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct DeviceState {
+  int checked = 0;  // 0 unknown, 1 ok, -1 bad
+  int num_sms = 0;
+  EncodeTiledFn encode = nullptr;
+  std::string why;
+};
+DeviceState g_dev;
+std::mutex g_mu;
+
+int ensure_device() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_dev.checked == 1) return WM_OK;
+  if (g_dev.checked == -1) return fail(WM_ERR_ARCH, "%s", g_dev.why.c_str());
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    g_dev.why = "no CUDA device";
+    g_dev.checked = -1;
+    return fail(WM_ERR_ARCH, "%s", g_dev.why.c_str());
+  }
+  if (prop.major != 10) {
+    char b[128];
+    snprintf(b, sizeof(b), "wm_b200 requires sm_100 (B200); found sm_%d%d -- there is no fallback path", prop.major,
+             prop.minor);
+    g_dev.why = b;
+    g_dev.checked = -1;
+    return fail(WM_ERR_ARCH, "%s", g_dev.why.c_str());
+  }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
+    g_dev.why = "cuTensorMapEncodeTiled not available from the driver";
+    g_dev.checked = -1;
+    return fail(WM_ERR_ARCH, "%s", g_dev.why.c_str());
+  }
+  g_dev.encode = reinterpret_cast<EncodeTiledFn>(fn);
+  g_dev.num_sms = prop.multiProcessorCount;
+  g_dev.checked = 1;
+  return WM_OK;
+}
+
+// bf16 tensor map, SWIZZLE_128B, inner box = 64 elements (128 bytes).  dims/strides innermost first.
+int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+             const uint32_t* box, const char* what) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(WM_ERR_ALIGN, "%s: base pointer not 16-byte aligned", what);
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      if (strides_bytes[i - 1] % 16 != 0) return fail(WM_ERR_ALIGN, "%s: stride %d not a multiple of 16 bytes", what, i);
+      gs[i - 1] = strides_bytes[i - 1];
+    }
+  }
+  CUresult r = g_dev.encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(WM_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+  return WM_OK;
+}
+
+int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                const char* what) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[1] = {ld * 2};
+  const uint32_t box[2] = {64, box_rows};
+  return make_map(m, ptr, 2, dims, strides, box, what);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int wm_version(void) { return 100; }
+const char* wm_last_error(void) { return g_err.c_str(); }
+int wm_device_check(void) { return ensure_device(); }
+
+int wm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
+                 int64_t ldr, int res_mod, void* out_bf16, int64_t ldc_bf16, float* out_f32, int64_t ldc_f32, int M,
+                 int N, int K, int act, int bn_hint, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (M <= 0 || N <= 0 || K <= 0) return fail(WM_ERR_SHAPE, "wm_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  if (K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0) return fail(WM_ERR_ALIGN, "wm_gemm_bf16: K, lda, ldw must be multiples of 8");
+  if (out_bf16 == nullptr && out_f32 == nullptr) return fail(WM_ERR_SHAPE, "wm_gemm_bf16: no output");
+  if (act < 0 || act > 3) return fail(WM_ERR_SHAPE, "wm_gemm_bf16: bad act %d", act);
+  if (residual != nullptr && res_mod <= 0) return fail(WM_ERR_SHAPE, "wm_gemm_bf16: res_mod must be > 0");
+  int bn = bn_hint;
+  if (bn == 0) bn = (N >= 256) ? 256 : (N > 64 ? 128 : 64);
+  if (bn != 64 && bn != 128 && bn != 256) return fail(WM_ERR_SHAPE, "wm_gemm_bf16: bn_hint must be 0/64/128/256");
+  CUtensorMap ta, tw;
+  if (int rc = make_map_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, "wm_gemm_bf16(A)")) return rc;
+  if (int rc = make_map_2d(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, "wm_gemm_bf16(W)")) return rc;
+  wm::GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.residual = residual; p.ldr = (int)ldr; p.res_mod = res_mod > 0 ? res_mod : 1;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldc_bf16 = (int)ldc_bf16;
+  p.out_f32 = out_f32; p.ldc_f32 = (int)ldc_f32;
+  p.act = act; p.a_mode = 0; p.conv_C = 0;
+  p.vec_ok = (bias == nullptr || aligned16(bias)) && (residual == nullptr || (aligned16(residual) && ldr % 4 == 0)) &&
+             (out_bf16 == nullptr || (aligned16(out_bf16) && ldc_bf16 % 8 == 0)) &&
+             (out_f32 == nullptr || (aligned16(out_f32) && ldc_f32 % 4 == 0));
+  return check_launch(wm::gemm_dispatch(ta, tw, p, bn, g_dev.num_sms, (cudaStream_t)stream), "wm_gemm_bf16");
+}
+
+int wm_conv3x3_nhwc_bf16(const void* X, const void* W, void* out_bf16, float* out_f32, int B, int C, int N,
+                         void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (B <= 0 || C % 64 != 0 || N <= 0 || N % 8 != 0) return fail(WM_ERR_SHAPE, "wm_conv3x3_nhwc_bf16: bad shape B=%d C=%d N=%d", B, C, N);
+  if (out_bf16 == nullptr && out_f32 == nullptr) return fail(WM_ERR_SHAPE, "wm_conv3x3_nhwc_bf16: no output");
+  const int bn = (N >= 256) ? 256 : (N > 64 ? 128 : 64);
+  CUtensorMap ta, tw;
+  const uint64_t dims[4] = {(uint64_t)C, 64, 64, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)C * 2 * 64, (uint64_t)C * 2 * 4096};
+  const uint32_t box[4] = {64, 64, 2, 1};
+  if (int rc = make_map(&ta, X, 4, dims, strides, box, "wm_conv3x3_nhwc_bf16(X)")) return rc;
+  if (int rc = make_map_2d(&tw, W, (uint64_t)N, (uint64_t)9 * C, (uint64_t)9 * C, (uint32_t)bn, "wm_conv3x3_nhwc_bf16(W)")) return rc;
+  wm::GemmParams p{};
+  p.M = B * 4096; p.N = N; p.K = 9 * C;
+  p.res_mod = 1;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldc_bf16 = N;
+  p.out_f32 = out_f32; p.ldc_f32 = N;
+  p.a_mode = 1; p.conv_C = C;
+  p.vec_ok = (out_bf16 == nullptr || aligned16(out_bf16)) && (out_f32 == nullptr || aligned16(out_f32));
+  return check_launch(wm::gemm_dispatch(ta, tw, p, bn, g_dev.num_sms, (cudaStream_t)stream), "wm_conv3x3_nhwc_bf16");
+}
+
+int wm_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, const float* add,
+                 int add_mod, void* y2_bf16, int rows, int D, float eps, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(y_bf16) || !aligned16(y_f32) ||
+      !aligned16(add) || !aligned16(y2_bf16))
+    return fail(WM_ERR_ALIGN, "wm_layernorm: pointers must be 16-byte aligned");
+  if (y2_bf16 != nullptr && (add == nullptr || add_mod <= 0)) return fail(WM_ERR_SHAPE, "wm_layernorm: y2 needs add/add_mod");
+  return check_launch(wm::layernorm_launch(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, add,
+                                           add_mod > 0 ? add_mod : 1, reinterpret_cast<__nv_bfloat16*>(y2_bf16), rows, D,
+                                           eps, (cudaStream_t)stream),
+                      "wm_layernorm");
+}
+
+int wm_patchify(const float* img, void* patches_bf16, void* gray_bf16, int B, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (B <= 0) return fail(WM_ERR_SHAPE, "wm_patchify: B=%d", B);
+  if (!aligned16(img) || !aligned16(patches_bf16) || !aligned16(gray_bf16)) return fail(WM_ERR_ALIGN, "wm_patchify: alignment");
+  return check_launch(wm::patchify_launch(img, reinterpret_cast<__nv_bfloat16*>(patches_bf16),
+                                          reinterpret_cast<__nv_bfloat16*>(gray_bf16), B, (cudaStream_t)stream),
+                      "wm_patchify");
+}
+
+int wm_transpose(const void* in, void* out, int batch, int R, int C, int elt_bytes, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (batch <= 0 || R <= 0 || C <= 0 || batch > 65535) return fail(WM_ERR_SHAPE, "wm_transpose: bad shape");
+  return check_launch(wm::transpose_launch(in, out, batch, R, C, elt_bytes, (cudaStream_t)stream), "wm_transpose");
+}
+
+int wm_hfc_finalize(const float* img, const float* low_t, void* patches_bf16, float* hfc_img, int B, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (B <= 0 || B > 65535) return fail(WM_ERR_SHAPE, "wm_hfc_finalize: B=%d", B);
+  return check_launch(wm::hfc_finalize_launch(img, low_t, reinterpret_cast<__nv_bfloat16*>(patches_bf16), hfc_img, B,
+                                              (cudaStream_t)stream),
+                      "wm_hfc_finalize");
+}
+
+int wm_add_cast(const float* a, const float* b, int b_mod, void* out_bf16, int rows, int D, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (!aligned16(a) || !aligned16(b) || !aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_add_cast: alignment");
+  return check_launch(wm::add_cast_launch(a, b, b_mod > 0 ? b_mod : 1, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, D,
+                                          (cudaStream_t)stream),
+                      "wm_add_cast");
+}
+
+int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, int q_col0, const void* k,
+                  int64_t k_rows, int64_t k_width, int64_t ldk, int k_col0, const void* v, int64_t v_rows,
+                  int64_t v_width, int64_t ldv, int v_col0, const void* rel_table, void* out_bf16, int64_t ldo, int B,
+                  int H, int Tq, int Tk, int hd, float scale, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (B <= 0 || H <= 0 || (hd != 64 && hd != 128)) return fail(WM_ERR_SHAPE, "wm_attn_flash: bad B/H/hd");
+  if (Tq % 128 || Tk % 128 || Tk < 128) return fail(WM_ERR_SHAPE, "wm_attn_flash: Tq, Tk must be multiples of 128");
+  if ((int64_t)B * Tq > q_rows || (int64_t)B * Tk > k_rows || (int64_t)B * Tk > v_rows) return fail(WM_ERR_SHAPE, "wm_attn_flash: rows");
+  if (q_col0 + H * hd > q_width || k_col0 + H * hd > k_width || v_col0 + H * hd > v_width) return fail(WM_ERR_SHAPE, "wm_attn_flash: columns");
+  if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || !aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_attn_flash: alignment");
+  if (B > 65535 || H > 65535) return fail(WM_ERR_SHAPE, "wm_attn_flash: grid too large");
+  CUtensorMap tq, tk, tv, trel;
+  if (int rc = make_map_2d(&tq, q, (uint64_t)q_rows, (uint64_t)q_width, (uint64_t)ldq, 128, "wm_attn_flash(q)")) return rc;
+  if (int rc = make_map_2d(&tk, k, (uint64_t)k_rows, (uint64_t)k_width, (uint64_t)ldk, 128, "wm_attn_flash(k)")) return rc;
+  if (int rc = make_map_2d(&tv, v, (uint64_t)v_rows, (uint64_t)v_width, (uint64_t)ldv, 128, "wm_attn_flash(v)")) return rc;
+  trel = tq;
+  if (rel_table != nullptr) {
+    if (hd != 64 || Tq != 4096 || Tk != 4096) return fail(WM_ERR_SHAPE, "wm_attn_flash: rel-pos needs hd=64, 64x64 tokens");
+    if (int rc = make_map_2d(&trel, rel_table, 256, 64, 64, 256, "wm_attn_flash(rel)")) return rc;
+  }
+  wm::FlashParams p{};
+  p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.scale = scale;
+  p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldo = (int)ldo;
+  p.use_relpos = rel_table != nullptr;
+  return check_launch(wm::flash_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash");
+}
+
+int wm_attn_window(const void* qkv, const void* rel_table, void* out_bf16, int B, int H, int D, float scale,
+                   void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (B <= 0 || B > 65535 || H <= 0 || D != H * 64) return fail(WM_ERR_SHAPE, "wm_attn_window: needs D == H*64 (hd = 64)");
+  if (!aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_attn_window: alignment");
+  CUtensorMap tq, tkv, trel;
+  const uint64_t W3 = (uint64_t)3 * D;
+  const uint64_t dims[4] = {W3, 64, 64, (uint64_t)B};
+  const uint64_t strides[3] = {W3 * 2, W3 * 2 * 64, W3 * 2 * 4096};
+  const uint32_t box_q[4] = {64, 16, 7, 1};
+  const uint32_t box_kv[4] = {64, 16, 14, 1};
+  if (int rc = make_map(&tq, qkv, 4, dims, strides, box_q, "wm_attn_window(q)")) return rc;
+  if (int rc = make_map(&tkv, qkv, 4, dims, strides, box_kv, "wm_attn_window(kv)")) return rc;
+  if (int rc = make_map_2d(&trel, rel_table, 64, 64, 64, 64, "wm_attn_window(rel)")) return rc;
+  wm::WindowParams p{};
+  p.B = B; p.H = H; p.scale = scale; p.D = D;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  return check_launch(wm::window_dispatch(tq, tkv, trel, p, (cudaStream_t)stream), "wm_attn_window");
+}
+
+int wm_attn_small(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out_bf16,
+                  int64_t ldo, int B, int H, int Tq, int Tk, int hd, float scale, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (B <= 0 || B > 65535 || H <= 0 || Tq <= 0 || Tk <= 0) return fail(WM_ERR_SHAPE, "wm_attn_small: bad shape");
+  return check_launch(wm::attn_small_launch(reinterpret_cast<const __nv_bfloat16*>(q), (int)ldq,
+                                            reinterpret_cast<const __nv_bfloat16*>(k), (int)ldk,
+                                            reinterpret_cast<const __nv_bfloat16*>(v), (int)ldv,
+                                            reinterpret_cast<__nv_bfloat16*>(out_bf16), (int)ldo, B, H, Tq, Tk, hd, scale,
+                                            (cudaStream_t)stream),
+                      "wm_attn_small");
+}
+
+int wm_postprocess(const float* logits, const float* boxes, const int64_t* sizes, float thr, int from_prob,
+                   float* packed, int32_t* query_idx, int32_t* counts, int B, int Q, int C1, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (B < 0 || Q <= 0) return fail(WM_ERR_SHAPE, "wm_postprocess: bad shape");
+  return check_launch(wm::postprocess_launch(logits, boxes, reinterpret_cast<const long long*>(sizes), thr, from_prob,
+                                             packed, query_idx, counts, B, Q, C1, (cudaStream_t)stream),
+                      "wm_postprocess");
+}
+
+int wm_sigmoid_topk(const float* logits, const float* boxes, float* prob_ws, int32_t* order_ws, float* scores,
+                    int32_t* labels, int32_t* query, float* out_boxes, int B, int Q, int C1, int C, int K,
+                    int from_prob, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (B < 0 || B > 65535 || Q <= 0 || C <= 0 || C > C1) return fail(WM_ERR_SHAPE, "wm_sigmoid_topk: bad shape");
+  if (!aligned16(boxes) || !aligned16(out_boxes)) return fail(WM_ERR_ALIGN, "wm_sigmoid_topk: alignment");
+  return check_launch(wm::sigmoid_topk_launch(logits, boxes, prob_ws, order_ws, scores, labels, query, out_boxes, B, Q, C1,
+                                              C, K, from_prob, (cudaStream_t)stream),
+                      "wm_sigmoid_topk");
+}
+
+int wm_nms(const float* boxes, const float* scores, const int64_t* labels, int n, double iou_thr, int32_t* order_ws,
+           uint64_t* mask_ws, int64_t* keep, int32_t* num_keep, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (n < 0) return fail(WM_ERR_SHAPE, "wm_nms: n < 0");
+  if (n > 0 && !aligned16(boxes)) return fail(WM_ERR_ALIGN, "wm_nms: boxes must be 16-byte aligned");
+  if ((size_t)((n + 63) / 64) * 8 > 40 * 1024) return fail(WM_ERR_SHAPE, "wm_nms: n too large for the on-chip bitmap");
+  return check_launch(wm::nms_launch(boxes, scores, reinterpret_cast<const long long*>(labels), n, iou_thr, order_ws,
+                                     reinterpret_cast<unsigned long long*>(mask_ws), reinterpret_cast<long long*>(keep),
+                                     num_keep, (cudaStream_t)stream),
+                      "wm_nms");
+}
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+// Post-process kernels (sm_100a), bit-exact integer stages:
+//   postprocess     PostProcess.forward, build_sam.py:219-258 (+ box_cxcywh_to_xyxy, utils/box_ops.py:9-13):
+//                   softmax over 8 logits -> max over the 7 real classes (first index wins) -> keep score > fp32(thr)
+//                   -> xyxy -> * [s0,s1,s0,s1]; compacted in query order into packed [B,Q,6] rows + counts
+//   sigmoid_topk    north-star extension: sigmoid over the 7 class logits, stable top-K over Q*7 (ties: lower index)
+//   nms             torchvision.ops.nms semantics as called at visualize_prediction.py:150-154 (+ per-class variant):
+//                   stable score-descending order, fp32 IoU with IEEE ops and no FMA contraction,
+//                   suppress iff (double)iou > (double)thr; 64x64 bitmask tiles + block-serial reduction.
+#include "common.cuh"
+#include "wm_internal.h"
+
+namespace wm {
+
+// ------------------------------------------------------------------ PostProcess
+// mode 0: logits -> softmax; mode 1: input already holds the class probabilities (integer-stage parity test)
+__global__ void __launch_bounds__(1024) postprocess_kernel(const float* __restrict__ in, const float* __restrict__ boxes,
+                                                           const long long* __restrict__ sizes, float thr, int mode,
+                                                           float* __restrict__ packed, int* __restrict__ query_idx,
+                                                           int* __restrict__ counts, int Q, int C1) {
+  __shared__ int warp_cnt[32];
+  __shared__ int base;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) base = 0;
+  const float s0 = (float)sizes[2 * b + 0], s1 = (float)sizes[2 * b + 1];  // img_w = sizes[0], img_h = sizes[1]
+  __syncthreads();
+  for (int q0 = 0; q0 < Q; q0 += 1024) {
+    const int q = q0 + threadIdx.x;
+    bool keep = false;
+    float score = 0.f;
+    int label = 0;
+    if (q < Q) {
+      const float* x = in + ((size_t)b * Q + q) * C1;
+      float pr[16];
+      if (mode == 0) {
+        float mx = x[0];
+        for (int c = 1; c < C1; ++c) mx = fmaxf(mx, x[c]);
+        float sum = 0.f;
+        for (int c = 0; c < C1; ++c) {
+          pr[c] = expf(x[c] - mx);
+          sum = __fadd_rn(sum, pr[c]);
+        }
+        for (int c = 0; c < C1; ++c) pr[c] = __fdiv_rn(pr[c], sum);
+      } else {
+        for (int c = 0; c < C1; ++c) pr[c] = x[c];
+      }
+      score = pr[0];
+      for (int c = 1; c < C1 - 1; ++c)
+        if (pr[c] > score) { score = pr[c]; label = c; }  // strict > : first maximum wins
+      keep = score > thr;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    off += __popc(bal & ((1u << lane) - 1));
+    if (keep) {
+      const float* bx = boxes + ((size_t)b * Q + q) * 4;
+      const float cx = bx[0], cy = bx[1], hw = __fmul_rn(0.5f, bx[2]), hh = __fmul_rn(0.5f, bx[3]);
+      float* o = packed + ((size_t)b * Q + off) * 6;
+      o[0] = __fmul_rn(__fsub_rn(cx, hw), s0);
+      o[1] = __fmul_rn(__fsub_rn(cy, hh), s1);
+      o[2] = __fmul_rn(__fadd_rn(cx, hw), s0);
+      o[3] = __fmul_rn(__fadd_rn(cy, hh), s1);
+      o[4] = score;
+      o[5] = (float)label;
+      query_idx[(size_t)b * Q + off] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 32; ++w) t += warp_cnt[w];
+      base += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[b] = base;
+}
+
+int postprocess_launch(const float* in, const float* boxes, const long long* sizes, float thr, int mode, float* packed,
+                       int* query_idx, int* counts, int B, int Q, int C1, cudaStream_t st) {
+  if (C1 < 2 || C1 > 16) return WM_ERR_SHAPE;
+  if (B == 0) return WM_OK;
+  postprocess_kernel<<<B, 1024, 0, st>>>(in, boxes, sizes, thr, mode, packed, query_idx, counts, Q, C1);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ stable descending rank (exact argsort, O(n^2))
+// rank[i] = #{ j : s[j] > s[i]  or  (s[j] == s[i] and j < i) };  order[rank[i]] = i.
+__global__ void __launch_bounds__(256) rank_desc_kernel(const float* __restrict__ s, int n, int* __restrict__ order,
+                                                        size_t batch_stride_s, size_t batch_stride_o) {
+  __shared__ float tile[1024];
+  const float* sb = s + blockIdx.y * batch_stride_s;
+  int* ob = order + blockIdx.y * batch_stride_o;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const float si = i < n ? sb[i] : 0.f;
+  int rank = 0;
+  for (int j0 = 0; j0 < n; j0 += 1024) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 1024; t += 256) tile[t] = (j0 + t < n) ? sb[j0 + t] : -INFINITY;
+    __syncthreads();
+    const int lim = min(1024, n - j0);
+    for (int t = 0; t < lim; ++t) {
+      const float sj = tile[t];
+      rank += (sj > si) || (sj == si && (j0 + t) < i);
+    }
+  }
+  if (i < n) ob[rank] = i;
+}
+
+// ------------------------------------------------------------------ sigmoid + top-K
+__global__ void __launch_bounds__(256) sigmoid_kernel(const float* __restrict__ logits, float* __restrict__ prob, int Q,
+                                                      int C1, int C, size_t total) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const size_t bq = i / C;
+  const int c = (int)(i % C);
+  const float x = logits[bq * C1 + c];
+  prob[i] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+
+__global__ void __launch_bounds__(256) topk_gather_kernel(const float* __restrict__ prob, const int* __restrict__ order,
+                                                          const float* __restrict__ boxes, int n, int K, int C, int Q,
+                                                          float* __restrict__ scores, int* __restrict__ labels,
+                                                          int* __restrict__ query, float* __restrict__ out_boxes) {
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= K) return;
+  const int idx = order[(size_t)b * n + r];
+  const int q = idx / C;
+  scores[(size_t)b * K + r] = prob[(size_t)b * n + idx];
+  labels[(size_t)b * K + r] = idx % C;
+  query[(size_t)b * K + r] = q;
+  const float4 bx = *reinterpret_cast<const float4*>(boxes + ((size_t)b * Q + q) * 4);
+  *reinterpret_cast<float4*>(out_boxes + ((size_t)b * K + r) * 4) = bx;
+}
+
+int sigmoid_topk_launch(const float* logits, const float* boxes, float* prob_ws, int* order_ws, float* scores,
+                        int* labels, int* query, float* out_boxes, int B, int Q, int C1, int C, int K,
+                        int from_prob, cudaStream_t st) {
+  const int n = Q * C;
+  if (K > n || K <= 0) return WM_ERR_SHAPE;
+  if (B == 0) return WM_OK;
+  const size_t total = (size_t)B * n;
+  if (!from_prob) sigmoid_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(logits, prob_ws, Q, C1, C, total);
+  rank_desc_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(prob_ws, n, order_ws, n, n);
+  topk_gather_kernel<<<dim3((K + 255) / 256, B), 256, 0, st>>>(prob_ws, order_ws, boxes, n, K, C, Q, scores, labels,
+                                                              query, out_boxes);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ NMS
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float area_a, float area_b, double thr) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return (double)iou > thr;  // fp32 IoU against the DOUBLE threshold; NaN -> false
+}
+
+// mask[i][jb] bit t set  <=>  sorted box (jb*64+t) is suppressed by sorted box i   (only j > i matter)
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ boxes, const int* __restrict__ order,
+                                                      const long long* __restrict__ labels, int n, double thr,
+                                                      unsigned long long* __restrict__ mask) {
+  const int row_blk = blockIdx.y, col_blk = blockIdx.x;
+  if (col_blk < row_blk) return;
+  __shared__ float4 cb[64];
+  __shared__ float ca[64];
+  __shared__ long long cl[64];
+  const int nblk = (n + 63) / 64;
+  const int cj = col_blk * 64 + threadIdx.x;
+  if (cj < n) {
+    const int oj = order[cj];
+    const float4 bx = *reinterpret_cast<const float4*>(boxes + (size_t)oj * 4);
+    cb[threadIdx.x] = bx;
+    ca[threadIdx.x] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+    cl[threadIdx.x] = labels ? labels[oj] : 0;
+  }
+  __syncthreads();
+  const int i = row_blk * 64 + threadIdx.x;
+  if (i >= n) return;
+  const int oi = order[i];
+  const float4 a = *reinterpret_cast<const float4*>(boxes + (size_t)oi * 4);
+  const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const long long la = labels ? labels[oi] : 0;
+  const int cols = min(64, n - col_blk * 64);
+  unsigned long long bits = 0;
+  const int start = (row_blk == col_blk) ? threadIdx.x + 1 : 0;
+  for (int t = start; t < cols; ++t)
+    if (cl[t] == la && iou_gt(a, cb[t], area_a, ca[t], thr)) bits |= 1ull << t;
+  mask[(size_t)i * nblk + col_blk] = bits;
+}
+
+// One block: walk the sorted boxes 64 at a time; warp 0 lane 0 resolves the in-block chain from the diagonal
+// words, then all threads OR the rows of the survivors into the running "removed" bitmap.
+__global__ void __launch_bounds__(256) nms_reduce_kernel(const unsigned long long* __restrict__ mask,
+                                                         const int* __restrict__ order, int n,
+                                                         long long* __restrict__ keep, int* __restrict__ num_keep) {
+  extern __shared__ unsigned long long removed[];  // nblk words
+  __shared__ unsigned long long alive_word;
+  __shared__ int kept_total;
+  const int nblk = (n + 63) / 64;
+  for (int w = threadIdx.x; w < nblk; w += 256) removed[w] = 0;
+  if (threadIdx.x == 0) kept_total = 0;
+  __syncthreads();
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int cnt = min(64, n - blk * 64);
+    if (threadIdx.x == 0) {
+      unsigned long long rem = removed[blk];
+      unsigned long long alive = 0;
+      int kt = kept_total;
+      for (int t = 0; t < cnt; ++t) {
+        if (!((rem >> t) & 1ull)) {
+          alive |= 1ull << t;
+          keep[kt++] = order[blk * 64 + t];
+          rem |= mask[(size_t)(blk * 64 + t) * nblk + blk];
+        }
+      }
+      alive_word = alive;
+      kept_total = kt;
+    }
+    __syncthreads();
+    const unsigned long long alive = alive_word;
+    for (int w = blk + 1 + threadIdx.x; w < nblk; w += 256) {
+      unsigned long long acc = removed[w];
+      unsigned long long a = alive;
+      while (a) {
+        const int t = __ffsll((long long)a) - 1;
+        a &= a - 1;
+        acc |= mask[(size_t)(blk * 64 + t) * nblk + w];
+      }
+      removed[w] = acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *num_keep = kept_total;
+}
+
+int nms_launch(const float* boxes, const float* scores, const long long* labels, int n, double thr, int* order_ws,
+               unsigned long long* mask_ws, long long* keep, int* num_keep, cudaStream_t st) {
+  if (n == 0) {
+    cudaMemsetAsync(num_keep, 0, sizeof(int), st);
+    return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+  }
+  const int nblk = (n + 63) / 64;
+  rank_desc_kernel<<<dim3((n + 255) / 256, 1), 256, 0, st>>>(scores, n, order_ws, 0, 0);
+  nms_mask_kernel<<<dim3(nblk, nblk), 64, 0, st>>>(boxes, order_ws, labels, n, thr, mask_ws);
+  nms_reduce_kernel<<<1, 256, nblk * sizeof(unsigned long long), st>>>(mask_ws, order_ws, n, keep, num_keep);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+}  // namespace wm

@@ -1,0 +1,55 @@
+// Internal declarations shared by the .cu translation units behind the C ABI (include/wm_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define WM_OK 0
+#define WM_ERR_SHAPE (-1)
+#define WM_ERR_ALIGN (-2)
+#define WM_ERR_ARCH (-3)
+#define WM_ERR_CUDA (-4)
+
+namespace wm {
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;      // [N] fp32 or null
+  const float* residual;  // fp32, row (m % res_mod), leading dim ldr; or null
+  int ldr, res_mod;
+  __nv_bfloat16* out_bf16;  // nullable
+  int ldc_bf16;
+  float* out_f32;  // nullable
+  int ldc_f32;
+  int act;     // 0 none, 1 erf-GELU, 2 ReLU
+  int vec_ok;  // 16-byte vector epilogue allowed (alignment verified on host)
+  int a_mode;  // 0: A is [M,K] row-major; 1: implicit 3x3 conv over NHWC [B,64,64,conv_C]
+  int conv_C;
+};
+
+int gemm_dispatch(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, int bn, int num_sms,
+                  cudaStream_t st);
+
+struct FlashParams {
+  // O[b, t, h*HD + d] = softmax_k( scale * q.k + bias ) v   over Tk keys, per (image b, head h)
+  int B, H, Tq, Tk;
+  float scale;  // applied to q.k (the rel-pos bias uses the unscaled q)
+  int q_col0, k_col0, v_col0;  // first column of head 0 inside the q / k / v tensor maps
+  __nv_bfloat16* out;
+  int ldo;
+  int use_relpos;  // global 64x64 grid decomposed rel-pos; tables via tmap_rel ([256, HD]: rows 0..126 Rh, 128..254 Rw)
+};
+int flash_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
+                   const FlashParams& p, int hd, cudaStream_t st);
+
+struct WindowParams {
+  int B, H;     // images, heads
+  float scale;
+  int D;        // embedding dim (q at col h*64, k at D + h*64, v at 2D + h*64 in the [B,64,64,3D] qkv tensor)
+  __nv_bfloat16* out;  // [B,64,64,D]
+};
+int window_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const WindowParams& p,
+                    cudaStream_t st);
+
+}  // namespace wm

@@ -1,0 +1,230 @@
+"""torch.library registration of the C-ABI kernels as ``torch.ops.wm_b200.*`` (CUDA dispatch key only).
+
+PyTorch here is plumbing: it owns device memory and streams; every op below passes raw device pointers to
+libwm_b200.so (ctypes) on ``torch.cuda.current_stream()``.  All ops write into caller-provided tensors
+(kernels never allocate), so they are declared as mutating ops returning ``()``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import lib as _lib
+
+_LIBRARY = torch.library.Library("wm_b200", "DEF")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: Optional[torch.Tensor], dtype, name: str, inner_contig: bool = True) -> None:
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _lib.WmError(f"{name}: expected a CUDA tensor (wildlifemapper_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.WmError(f"{name}: expected {dtype}, got {t.dtype}")
+    if inner_contig and t.dim() > 0 and t.numel() > 0 and t.stride(-1) != 1:
+        raise _lib.WmError(f"{name}: innermost dimension must be contiguous")
+
+
+def _define(schema: str, fn) -> None:
+    name = schema.split("(", 1)[0]
+    _LIBRARY.define(schema)
+    _LIBRARY.impl(name, fn, "CUDA")
+
+
+# ------------------------------------------------------------------ GEMM family
+def _gemm(a, w, bias, residual, res_mod, out_bf16, out_f32, act, bn_hint):
+    _chk(a, torch.bfloat16, "gemm.a"); _chk(w, torch.bfloat16, "gemm.w")
+    _chk(bias, torch.float32, "gemm.bias"); _chk(residual, torch.float32, "gemm.residual")
+    _chk(out_bf16, torch.bfloat16, "gemm.out_bf16"); _chk(out_f32, torch.float32, "gemm.out_f32")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, (a.shape, w.shape)
+    for o in (out_bf16, out_f32):
+        assert o is None or tuple(o.shape) == (M, N), (o.shape, M, N)
+    assert bias is None or bias.numel() == N
+    _lib.call("wm_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(residual),
+              0 if residual is None else residual.stride(0), int(res_mod), _ptr(out_bf16),
+              0 if out_bf16 is None else out_bf16.stride(0), _ptr(out_f32), 0 if out_f32 is None else out_f32.stride(0),
+              M, N, K, int(act), int(bn_hint), _stream())
+
+
+_define("gemm(Tensor a, Tensor w, Tensor? bias, Tensor? residual, int res_mod, Tensor(a!)? out_bf16, "
+        "Tensor(b!)? out_f32, int act, int bn_hint) -> ()", _gemm)
+
+
+def _conv3x3(x, w, out_bf16, out_f32):
+    _chk(x, torch.bfloat16, "conv3x3.x"); _chk(w, torch.bfloat16, "conv3x3.w")
+    assert x.is_contiguous() and w.is_contiguous()
+    B, H, W_, Cc = x.shape
+    assert H == 64 and W_ == 64
+    N = w.shape[0]
+    assert w.shape[1] == 9 * Cc
+    for o in (out_bf16, out_f32):
+        assert o is None or (o.is_contiguous() and o.numel() == B * 4096 * N)
+    _lib.call("wm_conv3x3_nhwc_bf16", x.data_ptr(), w.data_ptr(), _ptr(out_bf16), _ptr(out_f32), B, Cc, N, _stream())
+
+
+_define("conv3x3(Tensor x, Tensor w, Tensor(a!)? out_bf16, Tensor(b!)? out_f32) -> ()", _conv3x3)
+
+
+# ------------------------------------------------------------------ bandwidth kernels
+def _layernorm(x, gamma, beta, y_bf16, y_f32, add, add_mod, y2_bf16, eps):
+    _chk(x, torch.float32, "layernorm.x")
+    assert x.is_contiguous()
+    D = x.shape[-1]
+    rows = x.numel() // D
+    for t in (y_bf16, y_f32, y2_bf16):
+        assert t is None or (t.is_contiguous() and t.numel() == x.numel())
+    _chk(y_bf16, torch.bfloat16, "layernorm.y_bf16"); _chk(y_f32, torch.float32, "layernorm.y_f32")
+    _chk(y2_bf16, torch.bfloat16, "layernorm.y2_bf16"); _chk(add, torch.float32, "layernorm.add")
+    _chk(gamma, torch.float32, "layernorm.gamma"); _chk(beta, torch.float32, "layernorm.beta")
+    _lib.call("wm_layernorm", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(y_bf16), _ptr(y_f32), _ptr(add),
+              int(add_mod), _ptr(y2_bf16), rows, D, float(eps), _stream())
+
+
+_define("layernorm(Tensor x, Tensor gamma, Tensor beta, Tensor(a!)? y_bf16, Tensor(b!)? y_f32, Tensor? add, "
+        "int add_mod, Tensor(c!)? y2_bf16, float eps) -> ()", _layernorm)
+
+
+def _patchify(img, patches, gray):
+    _chk(img, torch.float32, "patchify.img"); _chk(patches, torch.bfloat16, "patchify.patches")
+    _chk(gray, torch.bfloat16, "patchify.gray")
+    assert img.is_contiguous() and tuple(img.shape[1:]) == (3, 1024, 1024), img.shape
+    B = img.shape[0]
+    assert patches.is_contiguous() and patches.numel() == B * 4096 * 768
+    assert gray is None or (gray.is_contiguous() and gray.numel() == B * 1024 * 1024)
+    _lib.call("wm_patchify", img.data_ptr(), patches.data_ptr(), _ptr(gray), B, _stream())
+
+
+_define("patchify(Tensor img, Tensor(a!) patches, Tensor(b!)? gray) -> ()", _patchify)
+
+
+def _transpose(x, out):
+    assert x.is_contiguous() and out.is_contiguous() and x.dim() == 3 and x.dtype == out.dtype
+    b, R, Cc = x.shape
+    assert out.numel() == x.numel()
+    _lib.call("wm_transpose", x.data_ptr(), out.data_ptr(), b, R, Cc, x.element_size(), _stream())
+
+
+_define("transpose(Tensor x, Tensor(a!) out) -> ()", _transpose)
+
+
+def _hfc_finalize(img, low_t, patches, hfc_img):
+    _chk(img, torch.float32, "hfc_finalize.img"); _chk(low_t, torch.float32, "hfc_finalize.low_t")
+    _chk(patches, torch.bfloat16, "hfc_finalize.patches"); _chk(hfc_img, torch.float32, "hfc_finalize.hfc_img")
+    B = img.shape[0]
+    assert img.is_contiguous() and low_t.is_contiguous() and low_t.numel() == B * 1024 * 1024
+    assert patches.is_contiguous() and patches.numel() == B * 4096 * 256
+    _lib.call("wm_hfc_finalize", img.data_ptr(), low_t.data_ptr(), patches.data_ptr(), _ptr(hfc_img), B, _stream())
+
+
+_define("hfc_finalize(Tensor img, Tensor low_t, Tensor(a!) patches, Tensor(b!)? hfc_img) -> ()", _hfc_finalize)
+
+
+def _add_cast(a, b, b_mod, out):
+    _chk(a, torch.float32, "add_cast.a"); _chk(b, torch.float32, "add_cast.b"); _chk(out, torch.bfloat16, "add_cast.out")
+    assert a.is_contiguous() and out.is_contiguous() and out.numel() == a.numel()
+    D = a.shape[-1]
+    _lib.call("wm_add_cast", a.data_ptr(), _ptr(b), int(b_mod), out.data_ptr(), a.numel() // D, D, _stream())
+
+
+_define("add_cast(Tensor a, Tensor? b, int b_mod, Tensor(a!) out) -> ()", _add_cast)
+
+
+# ------------------------------------------------------------------ attention
+def _attn_flash(q, q_col0, k, k_col0, v, v_col0, rel_table, out, B, H, Tq, Tk, hd, scale):
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _chk(t, torch.bfloat16, "attn_flash." + n)
+        assert t.dim() == 2
+    _chk(rel_table, torch.bfloat16, "attn_flash.rel_table")
+    assert rel_table is None or (rel_table.is_contiguous() and tuple(rel_table.shape) == (256, 64))
+    assert out.shape[0] >= B * Tq and out.shape[1] >= H * hd
+    _lib.call("wm_attn_flash", q.data_ptr(), q.shape[0], q.shape[1], q.stride(0), int(q_col0),
+              k.data_ptr(), k.shape[0], k.shape[1], k.stride(0), int(k_col0),
+              v.data_ptr(), v.shape[0], v.shape[1], v.stride(0), int(v_col0),
+              _ptr(rel_table), out.data_ptr(), out.stride(0), B, H, Tq, Tk, hd, float(scale), _stream())
+
+
+_define("attn_flash(Tensor q, int q_col0, Tensor k, int k_col0, Tensor v, int v_col0, Tensor? rel_table, "
+        "Tensor(a!) out, int B, int H, int Tq, int Tk, int hd, float scale) -> ()", _attn_flash)
+
+
+def _attn_window(qkv, rel_table, out, H, scale):
+    _chk(qkv, torch.bfloat16, "attn_window.qkv"); _chk(rel_table, torch.bfloat16, "attn_window.rel_table")
+    _chk(out, torch.bfloat16, "attn_window.out")
+    assert qkv.is_contiguous() and out.is_contiguous() and rel_table.is_contiguous()
+    D = out.shape[-1]
+    B = out.numel() // (4096 * D)
+    assert qkv.numel() == B * 4096 * 3 * D and tuple(rel_table.shape) == (64, 64)
+    _lib.call("wm_attn_window", qkv.data_ptr(), rel_table.data_ptr(), out.data_ptr(), B, H, D, float(scale), _stream())
+
+
+_define("attn_window(Tensor qkv, Tensor rel_table, Tensor(a!) out, int H, float scale) -> ()", _attn_window)
+
+
+def _attn_small(q, k, v, out, B, H, Tq, Tk, hd, scale):
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _chk(t, torch.bfloat16, "attn_small." + n)
+        assert t.dim() == 2
+    _lib.call("wm_attn_small", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+              out.data_ptr(), out.stride(0), B, H, Tq, Tk, hd, float(scale), _stream())
+
+
+_define("attn_small(Tensor q, Tensor k, Tensor v, Tensor(a!) out, int B, int H, int Tq, int Tk, int hd, "
+        "float scale) -> ()", _attn_small)
+
+
+# ------------------------------------------------------------------ post-process
+def _postprocess(logits, boxes, sizes, thr, from_prob, packed, query_idx, counts):
+    _chk(logits, torch.float32, "postprocess.logits"); _chk(boxes, torch.float32, "postprocess.boxes")
+    _chk(sizes, torch.int64, "postprocess.sizes"); _chk(packed, torch.float32, "postprocess.packed")
+    _chk(query_idx, torch.int32, "postprocess.query_idx"); _chk(counts, torch.int32, "postprocess.counts")
+    assert logits.is_contiguous() and boxes.is_contiguous() and sizes.is_contiguous() and packed.is_contiguous()
+    B, Q, C1 = logits.shape
+    assert tuple(boxes.shape) == (B, Q, 4) and tuple(sizes.shape) == (B, 2) and packed.numel() == B * Q * 6
+    _lib.call("wm_postprocess", logits.data_ptr(), boxes.data_ptr(), sizes.data_ptr(), float(thr), int(from_prob),
+              packed.data_ptr(), query_idx.data_ptr(), counts.data_ptr(), B, Q, C1, _stream())
+
+
+_define("postprocess(Tensor logits, Tensor boxes, Tensor sizes, float thr, int from_prob, Tensor(a!) packed, "
+        "Tensor(b!) query_idx, Tensor(c!) counts) -> ()", _postprocess)
+
+
+def _sigmoid_topk(logits, boxes, prob_ws, order_ws, scores, labels, query, out_boxes, C, K, from_prob):
+    B, Q, C1 = logits.shape
+    for t in (logits, boxes, prob_ws, order_ws, scores, labels, query, out_boxes):
+        assert t.is_cuda and t.is_contiguous()
+    assert prob_ws.numel() == B * Q * C and order_ws.numel() == B * Q * C
+    _lib.call("wm_sigmoid_topk", logits.data_ptr(), boxes.data_ptr(), prob_ws.data_ptr(), order_ws.data_ptr(),
+              scores.data_ptr(), labels.data_ptr(), query.data_ptr(), out_boxes.data_ptr(), B, Q, C1, int(C), int(K),
+              int(from_prob), _stream())
+
+
+_define("sigmoid_topk(Tensor logits, Tensor boxes, Tensor(a!) prob_ws, Tensor(b!) order_ws, Tensor(c!) scores, "
+        "Tensor(d!) labels, Tensor(e!) query, Tensor(f!) out_boxes, int C, int K, int from_prob) -> ()", _sigmoid_topk)
+
+
+def _nms(boxes, scores, labels, iou_thr, order_ws, mask_ws, keep, num_keep):
+    _chk(boxes, torch.float32, "nms.boxes"); _chk(scores, torch.float32, "nms.scores"); _chk(labels, torch.int64, "nms.labels")
+    _chk(order_ws, torch.int32, "nms.order_ws"); _chk(mask_ws, torch.int64, "nms.mask_ws")
+    _chk(keep, torch.int64, "nms.keep"); _chk(num_keep, torch.int32, "nms.num_keep")
+    n = boxes.shape[0]
+    assert boxes.is_contiguous() and scores.is_contiguous() and (labels is None or labels.is_contiguous())
+    assert mask_ws.numel() >= n * ((n + 63) // 64) and order_ws.numel() >= n and keep.numel() >= n
+    _lib.call("wm_nms", boxes.data_ptr(), scores.data_ptr(), _ptr(labels), n, float(iou_thr), order_ws.data_ptr(),
+              mask_ws.data_ptr(), keep.data_ptr(), num_keep.data_ptr(), _stream())
+
+
+_define("nms(Tensor boxes, Tensor scores, Tensor? labels, float iou_thr, Tensor(a!) order_ws, Tensor(b!) mask_ws, "
+        "Tensor(c!) keep, Tensor(d!) num_keep) -> ()", _nms)
+
+ops = torch.ops.wm_b200

@@ -63,10 +63,10 @@ int wm_conv3x3_nhwc_bf16(const void* X, const void* W, void* out_bf16, float* ou
 int wm_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, const float* add,
                  int add_mod, void* y2_bf16, int rows, int D, float eps, void* stream);
 
-/* NCHW fp32 tile batch [B,3,1024,1024] -> bf16 im2col rows [B*4096, 768] (k = c*256 + ky*16 + kx) for the
- * patch-embed GEMM (image_encoder.py:409-417) and, if gray != NULL, the bf16 grayscale plane [B,1024,1024]
- * (0.2989 R + 0.587 G + 0.114 B, network.py:41). */
-int wm_patchify(const float* img, void* patches_bf16, void* gray_bf16, int B, void* stream);
+/* NCHW fp32 tile batch [B,C,1024,1024] (C = 3 or 1) -> bf16 im2col rows [B*4096, C*256] (k = c*256 + ky*16 + kx)
+ * for the patch-embed / hfc-embed GEMMs (image_encoder.py:409-417, 442-450) and, if C == 3 and gray != NULL, the
+ * bf16 grayscale plane [B,1024,1024] (0.2989 R + 0.587 G + 0.114 B, network.py:41). */
+int wm_patchify(const float* img, void* patches_bf16, void* gray_bf16, int B, int C, void* stream);
 
 /* Batched 2-D transpose: in [batch, R, C] -> out [batch, C, R]; elt_bytes 2 or 4. */
 int wm_transpose(const void* in, void* out, int batch, int R, int C, int elt_bytes, void* stream);
@@ -105,10 +105,11 @@ int wm_attn_small(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
 
 /* PostProcess.forward (build_sam.py:219-258): logits fp32 [B,Q,C1] (C1 = classes + no-object), boxes fp32
  * [B,Q,4] cxcywh, sizes int64 [B,2].  packed fp32 [B,Q,6] = (x1,y1,x2,y2,score,label) compacted in query
- * order, query_idx int32 [B,Q], counts int32 [B].  from_prob != 0: `logits` already holds softmax
+ * order, query_idx int32 [B,Q], labels int64 [B,Q] (nullable), counts int32 [B].  from_prob != 0: `logits` already holds softmax
  * probabilities (integer-stage parity entry). */
 int wm_postprocess(const float* logits, const float* boxes, const int64_t* sizes, float thr, int from_prob,
-                   float* packed, int32_t* query_idx, int32_t* counts, int B, int Q, int C1, void* stream);
+                   float* packed, int32_t* query_idx, int64_t* labels, int32_t* counts, int B, int Q, int C1,
+                   void* stream);
 
 /* sigmoid over the first C of C1 logits, stable top-K over Q*C (ties: lower flat index first).
  * prob_ws fp32 [B,Q*C] (input when from_prob != 0), order_ws int32 [B,Q*C].
@@ -122,6 +123,13 @@ int wm_sigmoid_topk(const float* logits, const float* boxes, float* prob_ws, int
  * [n * ceil(n/64)].  keep int64 [n] (score-descending), num_keep int32 [1]. */
 int wm_nms(const float* boxes, const float* scores, const int64_t* labels, int n, double iou_thr, int32_t* order_ws,
            uint64_t* mask_ws, int64_t* keep, int32_t* num_keep, void* stream);
+
+/* Batched NMS over the packed PostProcess rows, one CTA per image, no host round trip (Q <= 1024):
+ * candidates = rows [0, counts[b]) with score > score_thr (visualize_prediction.py:150), then the same greedy NMS
+ * as wm_nms (per_class != 0: only same-label boxes suppress each other).  keep_idx int32 [B,Q]: kept row indices in
+ * score order; keep_cnt int32 [B]. */
+int wm_nms_batched(const float* packed, const int32_t* counts, int B, int Q, float score_thr, double iou_thr,
+                   int per_class, int32_t* keep_idx, int32_t* keep_cnt, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,7 @@
 out=${1:-gpurun_out/isolated.log}
 mkdir -p "$(dirname "$out")"
 : > "$out"
-groups=("gemm_matches" "gemm_epilogues or gemm_strided" "conv3x3" "layernorm or patchify or transpose or hfc_finalize or add_cast"
+groups=("nms_batched" "gemm_matches" "gemm_epilogues or gemm_strided" "conv3x3" "layernorm or patchify or transpose or hfc_finalize or add_cast"
         "attn_small" "attn_flash_plain" "attn_flash_global" "attn_window" "postprocess or sigmoid_topk" "nms")
 for g in "${groups[@]}"; do
   echo "=== group: $g" >> "$out"

@@ -237,7 +237,7 @@ def test_postprocess_golden(golden_dir):
         packed = torch.zeros(B, Q, 6, device=DEV)
         qidx = torch.zeros(B, Q, device=DEV, dtype=torch.int32)
         counts = torch.zeros(B, device=DEV, dtype=torch.int32)
-        ops.postprocess(logits, boxes, sizes, 0.05, 0, packed, qidx, counts)
+        ops.postprocess(logits, boxes, sizes, 0.05, 0, packed, qidx, None, counts)
         for i in range(B):
             n = int(counts[i])
             ref_l = g[f"c{case}.{i}.labels"]
@@ -248,11 +248,13 @@ def test_postprocess_golden(golden_dir):
         # integer stage fed the oracle's probabilities: labels, keep set and boxes bit-exact
         prob = opost.softmax_f32(g[f"c{case}.logits"])
         ref = opost.select_from_prob(prob, g[f"c{case}.boxes"], g[f"c{case}.sizes"], 0.05)
-        ops.postprocess(torch.from_numpy(prob).to(DEV), boxes, sizes, 0.05, 1, packed, qidx, counts)
+        lab = torch.zeros(B, Q, device=DEV, dtype=torch.int64)
+        ops.postprocess(torch.from_numpy(prob).to(DEV), boxes, sizes, 0.05, 1, packed, qidx, lab, counts)
         for i in range(B):
             n = int(counts[i])
             assert n == ref[i]["labels"].shape[0]
             np.testing.assert_array_equal(qidx[i, :n].cpu().numpy(), ref[i]["query"])
+            np.testing.assert_array_equal(lab[i, :n].cpu().numpy(), ref[i]["labels"])
             np.testing.assert_array_equal(packed[i, :n, 5].cpu().numpy().astype(np.int64), ref[i]["labels"])
             np.testing.assert_array_equal(packed[i, :n, 4].cpu().numpy(), ref[i]["scores"])
             np.testing.assert_array_equal(packed[i, :n, :4].cpu().numpy(), ref[i]["boxes"])
@@ -310,3 +312,27 @@ def test_nms_edges(golden_dir):
         b, s, l = opost.make_nms_problem(777, seed=seed, dup_scores=bool(seed % 2))
         np.testing.assert_array_equal(_run_nms(b, s, None), opost.nms(b, s, 0.4))
         np.testing.assert_array_equal(_run_nms(b, s, l), opost.batched_nms(b, s, l, 0.4))
+
+
+@pytest.mark.parametrize("per_class", [0, 1])
+def test_nms_batched_small_bit_exact(per_class):
+    B, Q = 5, 900
+    packed = np.zeros((B, Q, 6), np.float32)
+    counts = np.array([900, 513, 0, 1, 64], np.int32)
+    for b in range(B):
+        bx, sc, lb = opost.make_nms_problem(Q, seed=10 + b, dup_scores=bool(b % 2))
+        bx = bx * np.float32(0.25)  # crowd the boxes so plenty overlap
+        packed[b, :, :4], packed[b, :, 4], packed[b, :, 5] = bx, sc, lb
+    keep_idx = torch.zeros(B, Q, device=DEV, dtype=torch.int32)
+    keep_cnt = torch.zeros(B, device=DEV, dtype=torch.int32)
+    ops.nms_batched(torch.from_numpy(packed).to(DEV), torch.from_numpy(counts).to(DEV), 0.5, 0.4, per_class, keep_idx, keep_cnt)
+    for b in range(B):
+        n = counts[b]
+        rows = packed[b, :n]
+        cand = np.nonzero(rows[:, 4] > np.float32(0.5))[0]
+        if per_class:
+            ref = cand[opost.batched_nms(rows[cand, :4], rows[cand, 4], rows[cand, 5].astype(np.int64), 0.4)]
+        else:
+            ref = cand[opost.nms(rows[cand, :4], rows[cand, 4], 0.4)]
+        assert int(keep_cnt[b]) == ref.shape[0]
+        np.testing.assert_array_equal(keep_idx[b, :ref.shape[0]].cpu().numpy(), ref)

@@ -1,0 +1,151 @@
+"""End-to-end parity on the B200 through the drop-in ``segment_anything`` modules (which call the C ABI):
+the CUDA path vs (a) golden outputs minted from the unmodified reference and (b) the fp32 CPU oracle run on the
+same seeded weights and tiles.  Tolerances are the ones BASELINE.json / SURVEY.md section 8d state for bf16:
+logits max-abs <= 2e-2, boxes mean-L1 <= 1e-3 and max <= 5e-3 (normalised), encoder features reported against
+the 5e-2 / 6e-3 (max / mean) bf16 proxy."""
+import os
+import sys
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a GPU", allow_module_level=True)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "wildlifemapper_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+import segment_anything as sa  # noqa: E402  (the drop-in)
+from segment_anything.modeling import ImageEncoderViT, MaskDecoder, PromptEncoder, TwoWayTransformer  # noqa: E402
+from segment_anything.network import MedSAM  # noqa: E402
+from segment_anything.utils.misc import NestedTensor  # noqa: E402
+from make_golden import sample_positions  # noqa: E402
+from oracle import model as om  # noqa: E402
+from oracle.weights import MODEL_CONFIGS, make_state_dict, make_tiles  # noqa: E402
+
+DEV = "cuda"
+
+
+def build(model_type: str, num_queries: int = 51) -> MedSAM:
+    D, depth, heads, glob = MODEL_CONFIGS[model_type]
+    enc = ImageEncoderViT(depth=depth, embed_dim=D, img_size=1024, mlp_ratio=4,
+                          norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_heads=heads, patch_size=16,
+                          qkv_bias=True, use_rel_pos=True, global_attn_indexes=list(glob), window_size=14, out_chans=256)
+    pe = PromptEncoder(embed_dim=256, image_embedding_size=(64, 64), input_image_size=(1024, 1024), mask_in_chans=16)
+    dec = MaskDecoder(num_multimask_outputs=num_queries - 1,
+                      transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
+                      transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256)
+    m = MedSAM(image_encoder=enc, mask_decoder=dec, prompt_encoder=pe).eval()
+    m.load_state_dict(make_state_dict(model_type, seed=0, num_queries=num_queries), strict=True)
+    return m.to(DEV)
+
+
+def check_outputs(out, ref_logits, ref_boxes, tag):
+    dl = np.abs(out["pred_logits"].cpu().numpy() - ref_logits)
+    db = np.abs(out["pred_boxes"].cpu().numpy() - ref_boxes)
+    print(f"[{tag}] logits max-abs {dl.max():.3e}  boxes mean-L1 {db.mean():.3e} max {db.max():.3e}")
+    assert out["pred_logits"].dtype == torch.float32 and out["pred_boxes"].dtype == torch.float32
+    assert dl.max() <= 2e-2
+    assert db.mean() <= 1e-3 and db.max() <= 5e-3
+
+
+@pytest.mark.parametrize("tag,batch,nq", [("vit_t", 2, 51), ("vit_t_q900", 1, 900)])
+def test_tiny_model_vs_reference_golden(golden_dir, tag, batch, nq):
+    g = np.load(os.path.join(golden_dir, f"golden_model_{tag}.npz"))
+    model = build("vit_t", nq)
+    tiles = make_tiles(batch, seed=2).to(DEV)
+    with torch.no_grad():
+        out = model(NestedTensor(tiles, None), np.array([[0, 0, 1024, 1024]] * batch))
+    check_outputs(out, g["pred_logits"], g["pred_boxes"], tag)
+
+
+def test_vit_b_vs_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "golden_model_vit_b.npz"))
+    sam, _crit, post = sa.sam_model_registry["vit_b"]()
+    model = MedSAM(sam.image_encoder, sam.mask_decoder, sam.prompt_encoder).eval()
+    model.load_state_dict(make_state_dict("vit_b", seed=0), strict=True)
+    model = model.to(DEV)
+    tiles = make_tiles(1, seed=2).to(DEV)
+    with torch.no_grad():
+        mask = model.fft(NestedTensor(tiles, None))
+        feats = model.image_encoder(tiles, mask)
+        out = model(NestedTensor(tiles, None), None)
+    check_outputs(out, g["pred_logits"], g["pred_boxes"], "vit_b")
+    # encoder features [B,256,64,64] at the golden sample positions
+    f = feats.float().contiguous().view(-1)
+    got = f[torch.from_numpy(sample_positions(f.numel(), "features")).to(DEV)].cpu().numpy()
+    d = np.abs(got - g["features.samples"])
+    print(f"[vit_b] features max-abs {d.max():.3e} mean-abs {d.mean():.3e} (|ref| max {np.abs(g['features.samples']).max():.2f})")
+    assert d.max() <= 1e-1 and d.mean() <= 1.2e-2
+    # high-pass image vs the reference's FFT path
+    h = mask.float().contiguous().view(-1)
+    got = h[torch.from_numpy(sample_positions(h.numel(), "x_hfc")).to(DEV)].cpu().numpy()
+    assert np.abs(got - g["x_hfc.samples"]).max() <= 2e-2
+    # drop-in PostProcess on the CUDA outputs vs the reference PostProcess on the reference outputs
+    res = post["bbox"](out, torch.tensor([[1024, 1024]], device=DEV))
+    assert res[0]["labels"].dtype == torch.int64
+    n_ref = g["pp0.labels"].shape[0]
+    assert abs(res[0]["labels"].shape[0] - n_ref) <= 2  # scores near the 0.05 threshold may flip in bf16
+    if res[0]["labels"].shape[0] == n_ref:
+        assert (res[0]["labels"].cpu().numpy() == g["pp0.labels"]).mean() >= 0.9
+        assert np.abs(res[0]["boxes"].cpu().numpy() - g["pp0.boxes"]).max() <= 5e-3 * 1024
+
+
+def test_tiny_model_stage_parity_vs_oracle():
+    """Per-stage comparison against the CPU oracle on the same inputs (reports where error enters)."""
+    model = build("vit_t", 51)
+    sd = make_state_dict("vit_t", seed=0)
+    tiles = make_tiles(2, seed=2)
+    otaps = {}
+    oout = om.forward(sd, "vit_t", tiles, otaps)
+    eng = model.image_encoder.engine()
+    t = tiles.to(DEV)
+    taps = {}
+    with torch.no_grad():
+        a_patch, a_hfc, hfc_img = eng.highpass(t, want_image=True)
+        feat, featb = eng.encode(a_patch, a_hfc, 2, taps)
+        out = model(NestedTensor(t, None), None)
+    torch.cuda.synchronize()
+
+    def cmp(name, got, ref, tol_max):
+        d = (got.float().cpu().reshape(ref.shape) - ref).abs()
+        print(f"[stage {name}] max-abs {d.max():.3e} mean-abs {d.mean():.3e} |ref|max {ref.abs().max():.2f}")
+        assert d.max().item() <= tol_max, name
+
+    cmp("x_hfc", hfc_img, otaps["x_hfc"], 2e-2)
+    cmp("after_hfc", taps["after_hfc"], otaps["after_hfc"], 1e-1)
+    cmp("block0", taps["block0"], otaps["block0"], 1.5e-1)
+    cmp("block1", taps["block1"], otaps["block1"], 2e-1)
+    cmp("features", feat.view(2, 4096, 256).transpose(1, 2), otaps["features"].flatten(2), 1e-1)
+    cmp("logits", out["pred_logits"], oout["pred_logits"], 2e-2)
+    cmp("boxes", out["pred_boxes"], oout["pred_boxes"], 5e-3)
+
+
+def test_loader_like_tiles_and_determinism():
+    """768x768 content zero-padded into the tile (reference loader, utils/misc.py:50-64) + bitwise repeatability."""
+    model = build("vit_t", 51)
+    sd = make_state_dict("vit_t", seed=0)
+    tiles = make_tiles(1, seed=5, loader_like=True)
+    ref = om.forward(sd, "vit_t", tiles)
+    with torch.no_grad():
+        o1 = model(NestedTensor(tiles.to(DEV), None), None)
+        l1, b1 = o1["pred_logits"].clone(), o1["pred_boxes"].clone()
+        o2 = model(NestedTensor(tiles.to(DEV), None), None)
+    check_outputs({"pred_logits": l1, "pred_boxes": b1}, ref["pred_logits"].numpy(), ref["pred_boxes"].numpy(), "loader")
+    assert torch.equal(l1, o2["pred_logits"]) and torch.equal(b1, o2["pred_boxes"])
+
+
+def test_errors_are_loud():
+    model = build("vit_t", 51)
+    tiles = make_tiles(1, seed=2)
+    with pytest.raises(RuntimeError):  # CPU tensors: no fallback
+        with torch.no_grad():
+            model(NestedTensor(tiles, None), None)
+    t = tiles.to(DEV).requires_grad_(True)
+    with pytest.raises(RuntimeError):  # training path not implemented
+        model(NestedTensor(t, None), None)

@@ -10,18 +10,19 @@
 namespace wm {
 int layernorm_launch(const float*, const float*, const float*, __nv_bfloat16*, float*, const float*, int,
                      __nv_bfloat16*, int, int, float, cudaStream_t);
-int patchify_launch(const float*, __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t);
+int patchify_launch(const float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
 int transpose_launch(const void*, void*, int, int, int, int, cudaStream_t);
 int hfc_finalize_launch(const float*, const float*, __nv_bfloat16*, float*, int, cudaStream_t);
 int add_cast_launch(const float*, const float*, int, __nv_bfloat16*, int, int, cudaStream_t);
 int attn_small_launch(const __nv_bfloat16*, int, const __nv_bfloat16*, int, const __nv_bfloat16*, int, __nv_bfloat16*,
                       int, int, int, int, int, int, float, cudaStream_t);
-int postprocess_launch(const float*, const float*, const long long*, float, int, float*, int*, int*, int, int, int,
-                       cudaStream_t);
+int postprocess_launch(const float*, const float*, const long long*, float, int, float*, int*, long long*, int*, int,
+                       int, int, cudaStream_t);
 int sigmoid_topk_launch(const float*, const float*, float*, int*, float*, int*, int*, float*, int, int, int, int, int,
                         int, cudaStream_t);
 int nms_launch(const float*, const float*, const long long*, int, double, int*, unsigned long long*, long long*, int*,
                cudaStream_t);
+int nms_batched_small_launch(const float*, const int*, int, int, float, double, int, int*, int*, cudaStream_t);
 }  // namespace wm
 
 namespace {
@@ -192,12 +193,12 @@ int wm_layernorm(const float* x, const float* gamma, const float* beta, void* y_
                       "wm_layernorm");
 }
 
-int wm_patchify(const float* img, void* patches_bf16, void* gray_bf16, int B, void* stream) {
+int wm_patchify(const float* img, void* patches_bf16, void* gray_bf16, int B, int C, void* stream) {
   if (int rc = ensure_device()) return rc;
-  if (B <= 0) return fail(WM_ERR_SHAPE, "wm_patchify: B=%d", B);
+  if (B <= 0 || B > 65535 || (C != 1 && C != 3)) return fail(WM_ERR_SHAPE, "wm_patchify: B=%d C=%d", B, C);
   if (!aligned16(img) || !aligned16(patches_bf16) || !aligned16(gray_bf16)) return fail(WM_ERR_ALIGN, "wm_patchify: alignment");
   return check_launch(wm::patchify_launch(img, reinterpret_cast<__nv_bfloat16*>(patches_bf16),
-                                          reinterpret_cast<__nv_bfloat16*>(gray_bf16), B, (cudaStream_t)stream),
+                                          reinterpret_cast<__nv_bfloat16*>(gray_bf16), B, C, (cudaStream_t)stream),
                       "wm_patchify");
 }
 
@@ -284,11 +285,13 @@ int wm_attn_small(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
 }
 
 int wm_postprocess(const float* logits, const float* boxes, const int64_t* sizes, float thr, int from_prob,
-                   float* packed, int32_t* query_idx, int32_t* counts, int B, int Q, int C1, void* stream) {
+                   float* packed, int32_t* query_idx, int64_t* labels, int32_t* counts, int B, int Q, int C1,
+                   void* stream) {
   if (int rc = ensure_device()) return rc;
   if (B < 0 || Q <= 0) return fail(WM_ERR_SHAPE, "wm_postprocess: bad shape");
   return check_launch(wm::postprocess_launch(logits, boxes, reinterpret_cast<const long long*>(sizes), thr, from_prob,
-                                             packed, query_idx, counts, B, Q, C1, (cudaStream_t)stream),
+                                             packed, query_idx, reinterpret_cast<long long*>(labels), counts, B, Q, C1,
+                                             (cudaStream_t)stream),
                       "wm_postprocess");
 }
 
@@ -313,6 +316,15 @@ int wm_nms(const float* boxes, const float* scores, const int64_t* labels, int n
                                      reinterpret_cast<unsigned long long*>(mask_ws), reinterpret_cast<long long*>(keep),
                                      num_keep, (cudaStream_t)stream),
                       "wm_nms");
+}
+
+int wm_nms_batched(const float* packed, const int32_t* counts, int B, int Q, float score_thr, double iou_thr,
+                   int per_class, int32_t* keep_idx, int32_t* keep_cnt, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (B < 0 || Q <= 0 || Q > 1024) return fail(WM_ERR_SHAPE, "wm_nms_batched: needs 0 < Q <= 1024 (use wm_nms for larger sets)");
+  return check_launch(wm::nms_batched_small_launch(packed, counts, B, Q, score_thr, iou_thr, per_class, keep_idx, keep_cnt,
+                                                   (cudaStream_t)stream),
+                      "wm_nms_batched");
 }
 
 }  // extern "C"

@@ -83,37 +83,43 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, __nv
 }
 
 // ------------------------------------------------------------------ patchify (+ grayscale)
-// One block per (image, patch row py): reads 3 x 16 x 1024 fp32 (coalesced rows), writes 64 patches x 768 bf16.
+// One block per (image, patch row py): reads C x 16 x 1024 fp32 (coalesced rows), writes 64 patches x C*256 bf16.
+template <int C>
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ patches,
                                                        __nv_bfloat16* __restrict__ gray) {
   const int b = blockIdx.y, py = blockIdx.x;
-  const float* base = img + (size_t)b * 3 * 1024 * 1024 + (size_t)py * 16 * 1024;
+  const float* base = img + (size_t)b * C * 1024 * 1024 + (size_t)py * 16 * 1024;
   // each thread handles 4 consecutive pixels (x4 = 0..255) of each of the 16 rows
   const int x4 = threadIdx.x;  // 256 threads x 4 px = 1024
   const int px = x4 >> 2, kx = (x4 & 3) * 4;
   for (int ky = 0; ky < 16; ++ky) {
-    float4 c[3];
+    float4 c[C];
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch)
+    for (int ch = 0; ch < C; ++ch)
       c[ch] = __ldg(reinterpret_cast<const float4*>(base + (size_t)ch * 1024 * 1024 + ky * 1024) + x4);
-    __nv_bfloat16* prow = patches + ((size_t)(b * 64 + py) * 64 + px) * 768 + ky * 16 + kx;
+    __nv_bfloat16* prow = patches + ((size_t)(b * 64 + py) * 64 + px) * (C * 256) + ky * 16 + kx;
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch)
+    for (int ch = 0; ch < C; ++ch)
       *reinterpret_cast<uint2*>(prow + ch * 256) = make_uint2(pack_bf16(c[ch].x, c[ch].y), pack_bf16(c[ch].z, c[ch].w));
-    if (gray) {
+    if (C == 3 && gray) {
       float4 g;
-      g.x = 0.2989f * c[0].x + 0.587f * c[1].x + 0.114f * c[2].x;
-      g.y = 0.2989f * c[0].y + 0.587f * c[1].y + 0.114f * c[2].y;
-      g.z = 0.2989f * c[0].z + 0.587f * c[1].z + 0.114f * c[2].z;
-      g.w = 0.2989f * c[0].w + 0.587f * c[1].w + 0.114f * c[2].w;
+      g.x = 0.2989f * c[0].x + 0.587f * c[C > 1 ? 1 : 0].x + 0.114f * c[C > 2 ? 2 : 0].x;
+      g.y = 0.2989f * c[0].y + 0.587f * c[C > 1 ? 1 : 0].y + 0.114f * c[C > 2 ? 2 : 0].y;
+      g.z = 0.2989f * c[0].z + 0.587f * c[C > 1 ? 1 : 0].z + 0.114f * c[C > 2 ? 2 : 0].z;
+      g.w = 0.2989f * c[0].w + 0.587f * c[C > 1 ? 1 : 0].w + 0.114f * c[C > 2 ? 2 : 0].w;
       *reinterpret_cast<uint2*>(gray + ((size_t)b * 1024 + py * 16 + ky) * 1024 + x4 * 4) =
           make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
     }
   }
 }
 
-int patchify_launch(const float* img, __nv_bfloat16* patches, __nv_bfloat16* gray, int B, cudaStream_t st) {
-  patchify_kernel<<<dim3(64, B), 256, 0, st>>>(img, patches, gray);
+int patchify_launch(const float* img, __nv_bfloat16* patches, __nv_bfloat16* gray, int B, int C, cudaStream_t st) {
+  if (C == 3)
+    patchify_kernel<3><<<dim3(64, B), 256, 0, st>>>(img, patches, gray);
+  else if (C == 1)
+    patchify_kernel<1><<<dim3(64, B), 256, 0, st>>>(img, patches, nullptr);
+  else
+    return WM_ERR_SHAPE;
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 

@@ -16,7 +16,8 @@ namespace wm {
 __global__ void __launch_bounds__(1024) postprocess_kernel(const float* __restrict__ in, const float* __restrict__ boxes,
                                                            const long long* __restrict__ sizes, float thr, int mode,
                                                            float* __restrict__ packed, int* __restrict__ query_idx,
-                                                           int* __restrict__ counts, int Q, int C1) {
+                                                           long long* __restrict__ labels_out, int* __restrict__ counts,
+                                                           int Q, int C1) {
   __shared__ int warp_cnt[32];
   __shared__ int base;
   const int b = blockIdx.x;
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(1024) postprocess_kernel(const float* __restri
       o[4] = score;
       o[5] = (float)label;
       query_idx[(size_t)b * Q + off] = q;
+      if (labels_out) labels_out[(size_t)b * Q + off] = label;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -79,10 +81,10 @@ __global__ void __launch_bounds__(1024) postprocess_kernel(const float* __restri
 }
 
 int postprocess_launch(const float* in, const float* boxes, const long long* sizes, float thr, int mode, float* packed,
-                       int* query_idx, int* counts, int B, int Q, int C1, cudaStream_t st) {
+                       int* query_idx, long long* labels_out, int* counts, int B, int Q, int C1, cudaStream_t st) {
   if (C1 < 2 || C1 > 16) return WM_ERR_SHAPE;
   if (B == 0) return WM_OK;
-  postprocess_kernel<<<B, 1024, 0, st>>>(in, boxes, sizes, thr, mode, packed, query_idx, counts, Q, C1);
+  postprocess_kernel<<<B, 1024, 0, st>>>(in, boxes, sizes, thr, mode, packed, query_idx, labels_out, counts, Q, C1);
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
@@ -248,6 +250,76 @@ int nms_launch(const float* boxes, const float* scores, const long long* labels,
   rank_desc_kernel<<<dim3((n + 255) / 256, 1), 256, 0, st>>>(scores, n, order_ws, 0, 0);
   nms_mask_kernel<<<dim3(nblk, nblk), 64, 0, st>>>(boxes, order_ws, labels, n, thr, mask_ws);
   nms_reduce_kernel<<<1, 256, nblk * sizeof(unsigned long long), st>>>(mask_ws, order_ws, n, keep, num_keep);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ batched small NMS (one block per image)
+// Consumes the packed PostProcess rows directly: candidates = rows with score > score_thr (visualize_prediction.py:150),
+// visited in stable score-descending order, greedy suppression with the same IoU arithmetic as above.
+// keep_idx[b][0..keep_cnt[b]) = kept row indices (into the packed rows of image b) in score order.
+constexpr int NMS_SMALL_MAX = 1024;
+__global__ void __launch_bounds__(256) nms_batched_small_kernel(const float* __restrict__ packed,
+                                                                const int* __restrict__ counts, int Q, float score_thr,
+                                                                double iou_thr, int per_class,
+                                                                int* __restrict__ keep_idx, int* __restrict__ keep_cnt) {
+  __shared__ float4 sb[NMS_SMALL_MAX];
+  __shared__ float sa[NMS_SMALL_MAX];
+  __shared__ float ss[NMS_SMALL_MAX];
+  __shared__ int sl[NMS_SMALL_MAX];
+  __shared__ int order[NMS_SMALL_MAX];
+  __shared__ unsigned char alive[NMS_SMALL_MAX];
+  __shared__ int nv_s, nk_s;
+  const int b = blockIdx.x;
+  const int n = min(counts[b], Q);
+  const float* rows = packed + (size_t)b * Q * 6;
+  if (threadIdx.x == 0) { nv_s = 0; nk_s = 0; }
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float* r = rows + (size_t)i * 6;
+    sb[i] = make_float4(r[0], r[1], r[2], r[3]);
+    sa[i] = __fmul_rn(__fsub_rn(r[2], r[0]), __fsub_rn(r[3], r[1]));
+    ss[i] = r[4];
+    sl[i] = (int)r[5];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float si = ss[i];
+    if (si > score_thr) {
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const float sj = ss[j];
+        rank += (sj > score_thr) && ((sj > si) || (sj == si && j < i));
+      }
+      order[rank] = i;
+      alive[rank] = 1;
+      atomicAdd(&nv_s, 1);
+    }
+  }
+  __syncthreads();
+  const int nv = nv_s;
+  for (int r = 0; r < nv; ++r) {
+    if (alive[r]) {  // block-uniform: alive[r] is only written before the barrier that ends the previous round
+      const int i = order[r];
+      if (threadIdx.x == 0) keep_idx[(size_t)b * Q + nk_s++] = i;
+      const float4 bi = sb[i];
+      const float ai = sa[i];
+      const int li = sl[i];
+      for (int r2 = r + 1 + threadIdx.x; r2 < nv; r2 += 256) {
+        if (alive[r2]) {
+          const int j = order[r2];
+          if ((!per_class || sl[j] == li) && iou_gt(bi, sb[j], ai, sa[j], iou_thr)) alive[r2] = 0;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) keep_cnt[b] = nk_s;
+}
+
+int nms_batched_small_launch(const float* packed, const int* counts, int B, int Q, float score_thr, double iou_thr,
+                             int per_class, int* keep_idx, int* keep_cnt, cudaStream_t st) {
+  if (Q > NMS_SMALL_MAX) return WM_ERR_SHAPE;
+  if (B == 0) return WM_OK;
+  nms_batched_small_kernel<<<B, 256, 0, st>>>(packed, counts, Q, score_thr, iou_thr, per_class, keep_idx, keep_cnt);
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 

@@ -22,7 +22,7 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-from .ops import ops
+from .profiler import ops
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 GRID = 64
@@ -257,21 +257,22 @@ class DecoderEngine:
         self.device = torch.device(device)
         self.ws = _Workspace(self.device)
         self.w: Dict[str, torch.Tensor] = {}
-        self.Q = 0
         self.launches = 0
 
-    def prepare(self, sd: Dict[str, torch.Tensor], gaussian_matrix: torch.Tensor) -> None:
-        """sd: MaskDecoder.state_dict(); gaussian_matrix: prompt_encoder.pe_layer buffer [2,128]."""
-        dev, w = self.device, self.w
-        g = lambda k: sd[k].to(dev)
-        # D1: dense positional encoding, constant per model (pos_encoder.py:24-33,50-70), token-major [4096,256]
-        G = gaussian_matrix.to(dev).float()
-        c = (torch.arange(GRID, device=dev, dtype=torch.float32) + 0.5) / GRID
+    @staticmethod
+    def dense_pe_tokens(gaussian_matrix: torch.Tensor) -> torch.Tensor:
+        """D1: PositionEmbeddingRandom over the 64x64 grid (pos_encoder.py:24-33,50-70), token-major [4096,256].
+        Constant per model: evaluated once at load time, not part of the per-tile path."""
+        G = gaussian_matrix.float()
+        c = (torch.arange(GRID, device=G.device, dtype=torch.float32) + 0.5) / GRID
         xy = torch.stack([c[None, :].expand(GRID, GRID), c[:, None].expand(GRID, GRID)], dim=-1)
         ang = 2 * math.pi * ((2 * xy - 1) @ G)
-        w["pe"] = torch.cat([torch.sin(ang), torch.cos(ang)], dim=-1).reshape(NTOK, 256).contiguous()
-        w["tokens"] = _f32(g("mask_tokens.weight"))
-        self.Q = w["tokens"].shape[0]
+        return torch.cat([torch.sin(ang), torch.cos(ang)], dim=-1).reshape(NTOK, 256).contiguous()
+
+    def prepare_transformer(self, sd: Dict[str, torch.Tensor], prefix: str = "") -> None:
+        """sd: TwoWayTransformer.state_dict() (prefix '') or MaskDecoder.state_dict() (prefix 'transformer.')."""
+        dev, w = self.device, self.w
+        g = lambda k: sd[prefix + k].to(dev)
 
         def attn(dst: str, src: str) -> None:
             for n in ("q", "k", "v", "out"):
@@ -279,7 +280,7 @@ class DecoderEngine:
                 w[f"{dst}.{n}_b"] = _f32(g(f"{src}.{n}_proj.bias"))
 
         for i in range(2):
-            L = f"transformer.layers.{i}."
+            L = f"layers.{i}."
             attn(f"l{i}.self", L + "self_attn")
             attn(f"l{i}.t2i", L + "cross_attn_token_to_image")
             attn(f"l{i}.i2t", L + "cross_attn_image_to_token")
@@ -287,15 +288,20 @@ class DecoderEngine:
                 w[f"l{i}.{n}_g"], w[f"l{i}.{n}_b"] = _f32(g(L + n + ".weight")), _f32(g(L + n + ".bias"))
             w[f"l{i}.lin1_w"], w[f"l{i}.lin1_b"] = _bf(g(L + "mlp.lin1.weight")), _f32(g(L + "mlp.lin1.bias"))
             w[f"l{i}.lin2_w"], w[f"l{i}.lin2_b"] = _bf(g(L + "mlp.lin2.weight")), _f32(g(L + "mlp.lin2.bias"))
-        attn("final", "transformer.final_attn_token_to_image")
-        w["nf_g"], w["nf_b"] = _f32(g("transformer.norm_final_attn.weight")), _f32(g("transformer.norm_final_attn.bias"))
+        attn("final", "final_attn_token_to_image")
+        w["nf_g"], w["nf_b"] = _f32(g("norm_final_attn.weight")), _f32(g("norm_final_attn.bias"))
+
+    def prepare_heads(self, sd: Dict[str, torch.Tensor]) -> None:
+        """sd: MaskDecoder.state_dict()."""
+        dev, w = self.device, self.w
+        w["tokens"] = _f32(sd["mask_tokens.weight"].to(dev))
         for head in ("class_embed", "bbox_embed"):
             for i in range(3):
-                w[f"{head}.{i}_w"] = _bf(g(f"{head}.layers.{i}.weight"))
-                w[f"{head}.{i}_b"] = _f32(g(f"{head}.layers.{i}.bias"))
+                w[f"{head}.{i}_w"] = _bf(sd[f"{head}.layers.{i}.weight"].to(dev))
+                w[f"{head}.{i}_b"] = _f32(sd[f"{head}.layers.{i}.bias"].to(dev))
 
     def _attention(self, pre: str, q_in, k_in, v_in, B: int, Tq: int, Tk: int, name: str) -> torch.Tensor:
-        """transformer.py:218-240: projections -> 8-head attention -> (returns pre-out_proj rows bf16)."""
+        """transformer.py:218-240: projections -> 8-head attention (returns the pre-out_proj rows, bf16)."""
         w, ws = self.w, self.ws
         C = w[pre + ".q_w"].shape[0]
         bf = torch.bfloat16
@@ -311,26 +317,30 @@ class DecoderEngine:
         self.launches += 4
         return o
 
-    def decode(self, feat: torch.Tensor, featb: torch.Tensor, B: int, taps: Optional[dict] = None):
-        """feat fp32 / featb bf16: NHWC encoder features [B*4096,256]. Returns (logits [B,Q,8], boxes [B,Q,4]) fp32."""
-        w, ws, Q = self.w, self.ws, self.Q
+    def transformer(self, feat: torch.Tensor, pe: torch.Tensor, tokens: torch.Tensor, B: int, Q: int):
+        """TwoWayTransformer.forward (transformer.py:62-106) on token-major rows.
+
+        feat fp32 [B*4096,256] (image embedding), pe fp32 [4096,256] (shared) or [B*4096,256], tokens fp32 [Q,256]
+        (batch-broadcast point embedding) or [B*Q,256].  Returns (queries fp32 [B*Q,256], its bf16 copy, keys fp32).
+        """
+        w, ws = self.w, self.ws
         bf, f32 = torch.bfloat16, torch.float32
         MQ, MK = B * Q, B * NTOK
-        tokens, pe = w["tokens"], w["pe"]
-        # queries = tokens (batch broadcast); bf16 operand copies: plain and "+ query_pe" (query_pe = tokens)
+        tmod, pmod = tokens.shape[0], pe.shape[0]
         X = ws.get("X", (MQ, 256), f32)
         Xb = ws.get("Xb", (MQ, 256), bf)
         Xpe = ws.get("Xpe", (MQ, 256), bf)
         keys = ws.get("keys", (MK, 256), f32)
         keysb = ws.get("keysb", (MK, 256), bf)
         keyspe = ws.get("keyspe", (MK, 256), bf)
+        Y = ws.get("Y", (MQ, 256), f32)
         zero = ws.get("zeroX", (MQ, 256), f32)
         zero.zero_()
-        ops.add_cast(zero, tokens, Q, Xb)  # Xb = bf16(tokens) broadcast over the batch
-        ops.add_cast(feat, pe, NTOK, keyspe)
-        keys_f32, keys_b = feat, featb
-        Y = ws.get("Y", (MQ, 256), f32)
-        self.launches += 2
+        ops.add_cast(zero, tokens, tmod, Xb)  # queries = point_embedding (bf16 operand copy)
+        ops.add_cast(feat, None, 0, keysb)
+        ops.add_cast(feat, pe, pmod, keyspe)
+        keys_f32 = feat
+        self.launches += 4
         for i in range(2):
             L = f"l{i}"
             if i == 0:  # skip_first_layer_pe: q = k = v = queries, output REPLACES the queries (transformer.py:155-156)
@@ -339,37 +349,42 @@ class DecoderEngine:
             else:
                 o = self._attention(L + ".self", Xpe, Xpe, Xb, B, Q, Q, "self")
                 _gemm(o, w[L + ".self.out_w"], w[L + ".self.out_b"], X, MQ, out_f32=Y)
-            ops.layernorm(Y, w[L + ".norm1_g"], w[L + ".norm1_b"], Xb, X, tokens, Q, Xpe, 1e-5)
+            ops.layernorm(Y, w[L + ".norm1_g"], w[L + ".norm1_b"], Xb, X, tokens, tmod, Xpe, 1e-5)
             # tokens -> image cross attention
-            o = self._attention(L + ".t2i", Xpe, keyspe, keys_b, B, Q, NTOK, "t2i")
+            o = self._attention(L + ".t2i", Xpe, keyspe, keysb, B, Q, NTOK, "t2i")
             _gemm(o, w[L + ".t2i.out_w"], w[L + ".t2i.out_b"], X, MQ, out_f32=Y)
             ops.layernorm(Y, w[L + ".norm2_g"], w[L + ".norm2_b"], Xb, X, None, 0, None, 1e-5)
             # MLP
             hid = ws.get("hid", (MQ, 2048), bf)
             _gemm(Xb, w[L + ".lin1_w"], w[L + ".lin1_b"], out_bf16=hid, act=ACT_RELU)
             _gemm(hid, w[L + ".lin2_w"], w[L + ".lin2_b"], X, MQ, out_f32=Y)
-            ops.layernorm(Y, w[L + ".norm3_g"], w[L + ".norm3_b"], Xb, X, tokens, Q, Xpe, 1e-5)
+            ops.layernorm(Y, w[L + ".norm3_g"], w[L + ".norm3_b"], Xb, X, tokens, tmod, Xpe, 1e-5)
             # image -> tokens cross attention (updates the keys)
             o = self._attention(L + ".i2t", keyspe, Xpe, Xb, B, NTOK, Q, "i2t")
             ky = ws.get("keysY", (MK, 256), f32)
             _gemm(o, w[L + ".i2t.out_w"], w[L + ".i2t.out_b"], keys_f32, MK, out_f32=ky)
-            ops.layernorm(ky, w[L + ".norm4_g"], w[L + ".norm4_b"], keysb, keys, pe, NTOK, keyspe, 1e-5)
-            keys_f32, keys_b = keys, keysb
+            ops.layernorm(ky, w[L + ".norm4_g"], w[L + ".norm4_b"], keysb, keys, pe, pmod, keyspe, 1e-5)
+            keys_f32 = keys
             self.launches += 9
-        o = self._attention("final", Xpe, keyspe, keys_b, B, Q, NTOK, "t2i")
+        o = self._attention("final", Xpe, keyspe, keysb, B, Q, NTOK, "t2i")
         _gemm(o, w["final.out_w"], w["final.out_b"], X, MQ, out_f32=Y)
         hs = ws.get("hs", (MQ, 256), f32)
         hsb = ws.get("hsb", (MQ, 256), bf)
         ops.layernorm(Y, w["nf_g"], w["nf_b"], hsb, hs, None, 0, None, 1e-5)
-        if taps is not None:
-            taps["hs"] = hs.clone().view(B, Q, 256)
-        logits = torch.empty(B, Q, 8, device=feat.device, dtype=f32)
-        boxes = torch.empty(B, Q, 4, device=feat.device, dtype=f32)
-        h1 = ws.get("head1", (MQ, 256), bf)
-        h2 = ws.get("head2", (MQ, 256), bf)
+        self.launches += 2
+        return hs, hsb, keys_f32
+
+    def heads(self, hsb: torch.Tensor, B: int, Q: int):
+        """class_embed / bbox_embed MLPs (box_decoder.py:102-103,154-176). Returns fp32 logits [B,Q,8], boxes [B,Q,4]."""
+        w, ws = self.w, self.ws
+        MQ = B * Q
+        logits = torch.empty(B, Q, 8, device=hsb.device, dtype=torch.float32)
+        boxes = torch.empty(B, Q, 4, device=hsb.device, dtype=torch.float32)
+        h1 = ws.get("head1", (MQ, 256), torch.bfloat16)
+        h2 = ws.get("head2", (MQ, 256), torch.bfloat16)
         for head, out, act in (("class_embed", logits, ACT_NONE), ("bbox_embed", boxes, ACT_SIGMOID)):
             _gemm(hsb, w[head + ".0_w"], w[head + ".0_b"], out_bf16=h1, act=ACT_RELU)
             _gemm(h1, w[head + ".1_w"], w[head + ".1_b"], out_bf16=h2, act=ACT_RELU)
             _gemm(h2, w[head + ".2_w"], w[head + ".2_b"], out_f32=out.view(MQ, -1), act=act)
-        self.launches += 8
+        self.launches += 6
         return logits, boxes

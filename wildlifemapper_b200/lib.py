@@ -22,7 +22,7 @@ SIGNATURES = {
     "wm_gemm_bf16": [_p, _i64, _p, _i64, _p, _p, _i64, _i, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _p],
     "wm_conv3x3_nhwc_bf16": [_p, _p, _p, _p, _i, _i, _i, _p],
     "wm_layernorm": [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _f, _p],
-    "wm_patchify": [_p, _p, _p, _i, _p],
+    "wm_patchify": [_p, _p, _p, _i, _i, _p],
     "wm_transpose": [_p, _p, _i, _i, _i, _i, _p],
     "wm_hfc_finalize": [_p, _p, _p, _p, _i, _p],
     "wm_add_cast": [_p, _p, _i, _p, _i, _i, _p],
@@ -30,9 +30,10 @@ SIGNATURES = {
                       _i, _i, _i, _i, _i, _f, _p],
     "wm_attn_window": [_p, _p, _p, _i, _i, _i, _f, _p],
     "wm_attn_small": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _f, _p],
-    "wm_postprocess": [_p, _p, _p, _f, _i, _p, _p, _p, _i, _i, _i, _p],
+    "wm_postprocess": [_p, _p, _p, _f, _i, _p, _p, _p, _p, _i, _i, _i, _p],
     "wm_sigmoid_topk": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "wm_nms": [_p, _p, _p, _i, _d, _p, _p, _p, _p, _p],
+    "wm_nms_batched": [_p, _p, _i, _i, _f, _d, _i, _p, _p, _p],
 }
 
 _lib = None

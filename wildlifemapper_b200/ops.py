@@ -98,11 +98,11 @@ _define("layernorm(Tensor x, Tensor gamma, Tensor beta, Tensor(a!)? y_bf16, Tens
 def _patchify(img, patches, gray):
     _chk(img, torch.float32, "patchify.img"); _chk(patches, torch.bfloat16, "patchify.patches")
     _chk(gray, torch.bfloat16, "patchify.gray")
-    assert img.is_contiguous() and tuple(img.shape[1:]) == (3, 1024, 1024), img.shape
-    B = img.shape[0]
-    assert patches.is_contiguous() and patches.numel() == B * 4096 * 768
-    assert gray is None or (gray.is_contiguous() and gray.numel() == B * 1024 * 1024)
-    _lib.call("wm_patchify", img.data_ptr(), patches.data_ptr(), _ptr(gray), B, _stream())
+    assert img.is_contiguous() and img.dim() == 4 and tuple(img.shape[2:]) == (1024, 1024), img.shape
+    B, Cc = img.shape[0], img.shape[1]
+    assert patches.is_contiguous() and patches.numel() == B * 4096 * 256 * Cc
+    assert gray is None or (Cc == 3 and gray.is_contiguous() and gray.numel() == B * 1024 * 1024)
+    _lib.call("wm_patchify", img.data_ptr(), patches.data_ptr(), _ptr(gray), B, Cc, _stream())
 
 
 _define("patchify(Tensor img, Tensor(a!) patches, Tensor(b!)? gray) -> ()", _patchify)
@@ -184,19 +184,21 @@ _define("attn_small(Tensor q, Tensor k, Tensor v, Tensor(a!) out, int B, int H, 
 
 
 # ------------------------------------------------------------------ post-process
-def _postprocess(logits, boxes, sizes, thr, from_prob, packed, query_idx, counts):
+def _postprocess(logits, boxes, sizes, thr, from_prob, packed, query_idx, labels, counts):
     _chk(logits, torch.float32, "postprocess.logits"); _chk(boxes, torch.float32, "postprocess.boxes")
     _chk(sizes, torch.int64, "postprocess.sizes"); _chk(packed, torch.float32, "postprocess.packed")
     _chk(query_idx, torch.int32, "postprocess.query_idx"); _chk(counts, torch.int32, "postprocess.counts")
+    _chk(labels, torch.int64, "postprocess.labels")
+    assert labels is None or (labels.is_contiguous() and labels.numel() == logits.shape[0] * logits.shape[1])
     assert logits.is_contiguous() and boxes.is_contiguous() and sizes.is_contiguous() and packed.is_contiguous()
     B, Q, C1 = logits.shape
     assert tuple(boxes.shape) == (B, Q, 4) and tuple(sizes.shape) == (B, 2) and packed.numel() == B * Q * 6
     _lib.call("wm_postprocess", logits.data_ptr(), boxes.data_ptr(), sizes.data_ptr(), float(thr), int(from_prob),
-              packed.data_ptr(), query_idx.data_ptr(), counts.data_ptr(), B, Q, C1, _stream())
+              packed.data_ptr(), query_idx.data_ptr(), _ptr(labels), counts.data_ptr(), B, Q, C1, _stream())
 
 
 _define("postprocess(Tensor logits, Tensor boxes, Tensor sizes, float thr, int from_prob, Tensor(a!) packed, "
-        "Tensor(b!) query_idx, Tensor(c!) counts) -> ()", _postprocess)
+        "Tensor(b!) query_idx, Tensor(c!)? labels, Tensor(d!) counts) -> ()", _postprocess)
 
 
 def _sigmoid_topk(logits, boxes, prob_ws, order_ws, scores, labels, query, out_boxes, C, K, from_prob):
@@ -226,5 +228,17 @@ def _nms(boxes, scores, labels, iou_thr, order_ws, mask_ws, keep, num_keep):
 
 _define("nms(Tensor boxes, Tensor scores, Tensor? labels, float iou_thr, Tensor(a!) order_ws, Tensor(b!) mask_ws, "
         "Tensor(c!) keep, Tensor(d!) num_keep) -> ()", _nms)
+
+def _nms_batched(packed, counts, score_thr, iou_thr, per_class, keep_idx, keep_cnt):
+    _chk(packed, torch.float32, "nms_batched.packed"); _chk(counts, torch.int32, "nms_batched.counts")
+    _chk(keep_idx, torch.int32, "nms_batched.keep_idx"); _chk(keep_cnt, torch.int32, "nms_batched.keep_cnt")
+    B, Q, six = packed.shape
+    assert six == 6 and packed.is_contiguous() and keep_idx.numel() == B * Q and keep_cnt.numel() == B
+    _lib.call("wm_nms_batched", packed.data_ptr(), counts.data_ptr(), B, Q, float(score_thr), float(iou_thr),
+              int(per_class), keep_idx.data_ptr(), keep_cnt.data_ptr(), _stream())
+
+
+_define("nms_batched(Tensor packed, Tensor counts, float score_thr, float iou_thr, int per_class, "
+        "Tensor(a!) keep_idx, Tensor(b!) keep_cnt) -> ()", _nms_batched)
 
 ops = torch.ops.wm_b200

@@ -1,0 +1,118 @@
+"""Model factory, registry and PostProcess with the reference names and signatures (reference
+``segment_anything/build_sam.py``).  The DETR loss (SetCriterion / HungarianMatcher) is training-only and out of
+scope of the tile-detection hot path: the factory returns a placeholder criterion that raises
+when called."""
+from functools import partial
+
+import torch
+from torch import nn
+
+from wildlifemapper_b200 import postprocess as _pp
+
+from .modeling import ImageEncoderViT, MaskDecoder, PromptEncoder, Sam, TwoWayTransformer
+
+
+def build_sam_vit_h(checkpoint=None, args=None):
+    return _build_sam(1280, 32, 16, [7, 15, 23, 31], checkpoint=checkpoint, args=args)
+
+
+build_sam = build_sam_vit_h
+
+
+def build_sam_vit_l(checkpoint=None, args=None):
+    return _build_sam(1024, 24, 16, [5, 11, 17, 23], checkpoint=checkpoint, args=args)
+
+
+def build_sam_vit_b(checkpoint=None, args=None):
+    return _build_sam(768, 12, 12, [2, 5, 8, 11], checkpoint=checkpoint, args=args)
+
+
+sam_model_registry = {
+    "default": build_sam_vit_h,
+    "vit_h": build_sam_vit_h,
+    "vit_l": build_sam_vit_l,
+    "vit_b": build_sam_vit_b,
+}
+
+
+class SetCriterion(nn.Module):
+    """Placeholder with the reference's name: the Hungarian-matched DETR loss (build_sam.py:62-210, matcher.py)
+    is training-only; calling it raises."""
+
+    def __init__(self, num_classes=7, matcher=None, weight_dict=None, eos_coef=0.1, losses=()):
+        super().__init__()
+        self.num_classes, self.matcher, self.eos_coef, self.losses = num_classes, matcher, eos_coef, list(losses)
+        self.weight_dict = dict(weight_dict or {})
+
+    def forward(self, outputs, targets):
+        raise NotImplementedError("SetCriterion (training loss) is outside the B200 inference hot path; "
+                                  "SURVEY.md section 8f lists it as a 'next' row")
+
+
+class PostProcess(nn.Module):
+    """Reference build_sam.py:212-258: softmax -> drop no-object -> max -> keep score > threshold ->
+    cxcywh->xyxy -> scale by [s0, s1, s0, s1] (s = target_sizes row; the reference's h/w swap is reproduced)."""
+
+    def __init__(self, confidence_threshold=0.05):
+        super().__init__()
+        self.confidence_threshold = confidence_threshold
+
+    @torch.no_grad()
+    def forward(self, outputs, target_sizes):
+        out_logits, out_bbox = outputs["pred_logits"], outputs["pred_boxes"]
+        assert len(out_logits) == len(target_sizes)
+        assert target_sizes.shape[1] == 2
+        packed, labels, _query, counts = _pp.postprocess_packed(out_logits, out_bbox, target_sizes,
+                                                                self.confidence_threshold)
+        results = []
+        for i, n in enumerate(counts.tolist()):  # one D2H read: result lengths are data dependent
+            if n == 0:  # same empty result as the reference (CPU tensors, build_sam.py:240-243)
+                results.append({"scores": torch.tensor([]), "labels": torch.tensor([]),
+                                "boxes": torch.tensor([]).reshape(0, 4)})
+                continue
+            results.append({"scores": packed[i, :n, 4], "labels": labels[i, :n], "boxes": packed[i, :n, :4]})
+        return results
+
+
+def _build_sam(encoder_embed_dim, encoder_depth, encoder_num_heads, encoder_global_attn_indexes, checkpoint=None,
+               args=None):
+    prompt_embed_dim = 256
+    image_size = 1024
+    vit_patch_size = 16
+    image_embedding_size = image_size // vit_patch_size
+    num_classes = 6 + 1
+    # reference hard-codes 50 (+1) queries (build_sam.py:296); ``args.num_queries`` is the dense-herd knob
+    num_queries = int(getattr(args, "num_queries", 51) or 51)
+    sam = Sam(
+        image_encoder=ImageEncoderViT(
+            depth=encoder_depth, embed_dim=encoder_embed_dim, img_size=image_size, mlp_ratio=4,
+            norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_heads=encoder_num_heads, patch_size=vit_patch_size,
+            qkv_bias=True, use_rel_pos=True, global_attn_indexes=encoder_global_attn_indexes, window_size=14,
+            out_chans=prompt_embed_dim),
+        prompt_encoder=PromptEncoder(embed_dim=prompt_embed_dim,
+                                     image_embedding_size=(image_embedding_size, image_embedding_size),
+                                     input_image_size=(image_size, image_size), mask_in_chans=16),
+        mask_decoder=MaskDecoder(
+            num_multimask_outputs=num_queries - 1,
+            transformer=TwoWayTransformer(depth=2, embedding_dim=prompt_embed_dim, mlp_dim=2048, num_heads=8),
+            transformer_dim=prompt_embed_dim, iou_head_depth=3, iou_head_hidden_dim=256),
+        pixel_mean=[123.675, 116.28, 103.53],
+        pixel_std=[58.395, 57.12, 57.375],
+    )
+    sam.eval()
+    if checkpoint is not None:
+        with open(checkpoint, "rb") as f:
+            state_dict = torch.load(f, map_location="cpu")
+        # keep only the transformer weights of the SAM mask decoder (reference build_sam.py:311-320)
+        for k in [p for p in list(state_dict.keys()) if "mask_decoder" in p and "transformer" not in p]:
+            del state_dict[k]
+        sam.load_state_dict(state_dict, strict=False)
+    weight_dict = {"loss_ce": 3, "loss_bbox": getattr(args, "bbox_loss_coef", 5),
+                   "loss_giou": getattr(args, "giou_loss_coef", 2)}
+    criterion = SetCriterion(num_classes, matcher=None, weight_dict=weight_dict,
+                             eos_coef=getattr(args, "eos_coef", 0.1), losses=["labels", "boxes", "cardinality"])
+    device = getattr(args, "device", None)
+    if device is not None:
+        criterion.to(device)
+    postprocessors = {"bbox": PostProcess(confidence_threshold=0.05)}
+    return sam, criterion, postprocessors

@@ -1,0 +1,168 @@
+"""ImageEncoderViT with the reference's constructor, ``forward(x, x_hfc)`` signature and ``state_dict`` keys
+(reference ``modeling/image_encoder.py``), executed by the sm_100a kernel schedule in
+``wildlifemapper_b200.engine.EncoderEngine``.  The sub-modules below only hold parameters under the reference
+names; no torch compute runs in the forward pass.
+"""
+from typing import Optional, Tuple, Type
+
+import torch
+import torch.nn as nn
+
+from wildlifemapper_b200.engine import EncoderEngine
+from wildlifemapper_b200.ops import ops
+
+from .common import LayerNorm2d, MLPBlock, _MSG, params_version, require_inference
+
+
+class PatchEmbed(nn.Module):
+    def __init__(self, kernel_size=(16, 16), stride=(16, 16), padding=(0, 0), in_chans: int = 3,
+                 embed_dim: int = 768) -> None:
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=kernel_size, stride=stride, padding=padding)
+
+    def forward(self, x):
+        raise NotImplementedError(_MSG.format("PatchEmbed"))
+
+
+class HfcEmbed(PatchEmbed):
+    def __init__(self, kernel_size=(16, 16), stride=(16, 16), padding=(0, 0), in_chans: int = 1,
+                 embed_dim: int = 1024) -> None:
+        super().__init__(kernel_size, stride, padding, in_chans, embed_dim)
+
+
+class CrossAttentionHfcPatch(nn.Module):
+    """Parameters of the HFC cross-attention branch (reference image_encoder.py:452-484)."""
+
+    def __init__(self, d_model=1024, hfc_dim=1024, nhead=8, dropout=0.1, dim_feedforward=1024, activation="relu",
+                 proj_dim=1024):
+        super().__init__()
+        if (hfc_dim, nhead, dim_feedforward, proj_dim) != (1024, 8, 1024, 1024):
+            raise NotImplementedError("the fused HFC branch is specialised to the reference's 1024/8/1024/1024 config")
+        self.proj_hfc = nn.Conv2d(hfc_dim, proj_dim, (1, 1))
+        self.proj_patch = nn.Conv2d(d_model, proj_dim, (1, 1))
+        self.cross_attn = nn.MultiheadAttention(proj_dim, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(proj_dim, dim_feedforward)
+        self.linear2 = nn.Linear(dim_feedforward, dim_feedforward)
+        self.norm1 = nn.LayerNorm(proj_dim)
+        self.norm2 = nn.LayerNorm(dim_feedforward)
+        self.embed_dim = d_model
+        self.proj_back = nn.Conv2d(dim_feedforward, d_model, (1, 1))
+        self.pos_embed = nn.Parameter(torch.zeros(1, proj_dim, 64, 64))
+
+    def forward(self, hfc_embed, patch_embed):
+        raise NotImplementedError(_MSG.format("CrossAttentionHfcPatch"))
+
+
+class Attention(nn.Module):
+    def __init__(self, dim: int, num_heads: int = 8, qkv_bias: bool = True, use_rel_pos: bool = False,
+                 rel_pos_zero_init: bool = True, input_size: Optional[Tuple[int, int]] = None) -> None:
+        super().__init__()
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.use_rel_pos = use_rel_pos
+        if self.use_rel_pos:
+            assert input_size is not None, "Input size must be provided if using relative positional encoding."
+            self.rel_pos_h = nn.Parameter(torch.zeros(2 * input_size[0] - 1, head_dim))
+            self.rel_pos_w = nn.Parameter(torch.zeros(2 * input_size[1] - 1, head_dim))
+
+    def forward(self, x):
+        raise NotImplementedError(_MSG.format("Attention"))
+
+
+class Block(nn.Module):
+    def __init__(self, dim: int, num_heads: int, mlp_ratio: float = 4.0, qkv_bias: bool = True,
+                 norm_layer: Type[nn.Module] = nn.LayerNorm, act_layer: Type[nn.Module] = nn.GELU,
+                 use_rel_pos: bool = False, rel_pos_zero_init: bool = True, window_size: int = 0,
+                 input_size: Optional[Tuple[int, int]] = None) -> None:
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, use_rel_pos=use_rel_pos,
+                              rel_pos_zero_init=rel_pos_zero_init,
+                              input_size=input_size if window_size == 0 else (window_size, window_size))
+        self.norm2 = norm_layer(dim)
+        self.mlp = MLPBlock(embedding_dim=dim, mlp_dim=int(dim * mlp_ratio), act=act_layer)
+        self.window_size = window_size
+
+    def forward(self, x):
+        raise NotImplementedError(_MSG.format("Block"))
+
+
+class ImageEncoderViT(nn.Module):
+    def __init__(self, img_size: int = 1024, patch_size: int = 16, in_chans: int = 3, embed_dim: int = 768,
+                 depth: int = 12, num_heads: int = 12, mlp_ratio: float = 4.0, out_chans: int = 256,
+                 qkv_bias: bool = True, norm_layer: Type[nn.Module] = nn.LayerNorm,
+                 act_layer: Type[nn.Module] = nn.GELU, use_abs_pos: bool = True, use_rel_pos: bool = False,
+                 rel_pos_zero_init: bool = True, window_size: int = 0,
+                 global_attn_indexes: Tuple[int, ...] = ()) -> None:
+        super().__init__()
+        if (img_size, patch_size, in_chans, out_chans) != (1024, 16, 3, 256) or int(mlp_ratio) != 4:
+            raise NotImplementedError("the fused encoder is specialised to 1024x1024 RGB tiles, patch 16, neck 256")
+        if not (use_abs_pos and use_rel_pos and qkv_bias and window_size == 14) or act_layer is not nn.GELU:
+            raise NotImplementedError("the fused encoder implements the reference factory configuration "
+                                      "(abs pos + rel pos + qkv bias + 14x14 windows + GELU), build_sam.py:274-288")
+        self.img_size = img_size
+        self.patch_embed = PatchEmbed((patch_size, patch_size), (patch_size, patch_size), in_chans=in_chans,
+                                      embed_dim=embed_dim)
+        self.hfc_embed = HfcEmbed((patch_size, patch_size), (patch_size, patch_size), in_chans=1, embed_dim=1024)
+        self.pos_embed: Optional[nn.Parameter] = nn.Parameter(
+            torch.zeros(1, img_size // patch_size, img_size // patch_size, embed_dim))
+        self.hfc_attn = CrossAttentionHfcPatch(d_model=embed_dim, hfc_dim=1024, nhead=8, dropout=0.1,
+                                               dim_feedforward=1024, activation="relu", proj_dim=1024)
+        self.blocks = nn.ModuleList()
+        for i in range(depth):
+            self.blocks.append(Block(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                                     norm_layer=norm_layer, act_layer=act_layer, use_rel_pos=use_rel_pos,
+                                     rel_pos_zero_init=rel_pos_zero_init,
+                                     window_size=window_size if i not in global_attn_indexes else 0,
+                                     input_size=(img_size // patch_size, img_size // patch_size)))
+        for blk in self.blocks:
+            eps = getattr(blk.norm1, "eps", None)
+            if eps is None or abs(eps - 1e-6) > 1e-12:
+                raise NotImplementedError("block LayerNorm eps must be 1e-6 (build_sam.py:280)")
+        self.neck = nn.Sequential(
+            nn.Conv2d(embed_dim, out_chans, kernel_size=1, bias=False),
+            LayerNorm2d(out_chans),
+            nn.Conv2d(out_chans, out_chans, kernel_size=3, padding=1, bias=False),
+            LayerNorm2d(out_chans),
+        )
+        self._cfg = (embed_dim, depth, num_heads, tuple(global_attn_indexes))
+        self._engine: Optional[EncoderEngine] = None
+        self._engine_key = None
+
+    # ------------------------------------------------------------------ engine plumbing
+    def engine(self) -> EncoderEngine:
+        dev = self.pos_embed.device
+        key = (dev, params_version(self))
+        if self._engine is None or self._engine.device != dev:
+            self._engine = EncoderEngine(*self._cfg, device=dev)
+            self._engine_key = None
+        if self._engine_key != key:
+            self._engine.prepare(self.state_dict())
+            self._engine_key = key
+        return self._engine
+
+    def forward(self, x: torch.Tensor, x_hfc=None) -> torch.Tensor:
+        """x [B,3,1024,1024] fp32, x_hfc [B,1,1024,1024] fp32 (MedSAM.fft output) -> [B,256,64,64] fp32."""
+        if x_hfc is None:
+            raise TypeError("ImageEncoderViT.forward requires x_hfc (the reference forward dereferences it, "
+                            "image_encoder.py:128)")
+        require_inference(self, x, x_hfc)
+        eng = self.engine()
+        x = x.contiguous().float()
+        B = x.shape[0]
+        cached = getattr(x_hfc, "_wm_rows", None)
+        if cached is not None and cached[0] == (x.data_ptr(), x._version):
+            a_patch, a_hfc = cached[1], cached[2]  # produced by MedSAM.fft in the same pass over the tile
+        else:
+            a_patch = eng.ws.get("a_patch", (B * 4096, 768), torch.bfloat16)
+            ops.patchify(x, a_patch, None)
+            a_hfc = eng.ws.get("a_hfc", (B * 4096, 256), torch.bfloat16)
+            ops.patchify(x_hfc.contiguous().float(), a_hfc, None)
+            eng.launches += 2
+        feat, featb = eng.encode(a_patch, a_hfc, B)
+        out = eng.to_nchw(feat, B)
+        out._wm_nhwc = (feat, featb)  # token-major copies for the decoder (avoids a transpose round trip)
+        return out

@@ -31,7 +31,10 @@ def gather_detections(packed: torch.Tensor, counts: torch.Tensor, keep_idx: Opti
         if t is None:
             return None
         out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
-        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        if t.is_cuda:
+            dist.all_gather_into_tensor(out, t.contiguous(), group=group)  # one NCCL all-gather
+        else:  # gloo (CPU tests of the host logic)
+            dist.all_gather(list(out.chunk(world, dim=0)), t.contiguous(), group=group)
         return out
 
     return ag(packed), ag(counts), ag(keep_idx), ag(keep_cnt)

@@ -39,6 +39,9 @@ int wm_version(void);
 const char* wm_last_error(void);
 /* 0 if the current device is sm_100 and the driver exposes cuTensorMapEncodeTiled */
 int wm_device_check(void);
+/* Select the flash-attention kernel generation used by wm_attn_flash: 2 (default; two query tiles per CTA, O in
+ * TMEM, lazy rescaling) or 1 (first-generation kernel, kept for A/B measurements and Tq % 256 != 0). */
+int wm_set_flash_version(int version);
 
 /* C[M,N] = act(A[M,K] * W[N,K]^T + bias) + residual[(m % res_mod), :]      (tcgen05 / TMEM / TMA)
  * Replaces every nn.Linear / 1x1 Conv2d / patch-embed Conv2d(k16,s16) on the path:

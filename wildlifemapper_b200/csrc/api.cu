@@ -121,6 +121,8 @@ int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, u
   return make_map(m, ptr, 2, dims, strides, box, what);
 }
 
+int g_flash_version = 2;
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -130,6 +132,11 @@ extern "C" {
 int wm_version(void) { return 100; }
 const char* wm_last_error(void) { return g_err.c_str(); }
 int wm_device_check(void) { return ensure_device(); }
+int wm_set_flash_version(int version) {
+  if (version != 1 && version != 2) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 1 or 2");
+  g_flash_version = version;
+  return WM_OK;
+}
 
 int wm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
                  int64_t ldr, int res_mod, void* out_bf16, int64_t ldc_bf16, float* out_f32, int64_t ldc_f32, int M,
@@ -235,20 +242,23 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   if (q_col0 + H * hd > q_width || k_col0 + H * hd > k_width || v_col0 + H * hd > v_width) return fail(WM_ERR_SHAPE, "wm_attn_flash: columns");
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || !aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_attn_flash: alignment");
   if (B > 65535 || H > 65535) return fail(WM_ERR_SHAPE, "wm_attn_flash: grid too large");
+  const bool v2 = (g_flash_version == 2) && (Tq % 256 == 0);
+  const uint32_t kv_box = v2 ? 64 : 128;
   CUtensorMap tq, tk, tv, trel;
   if (int rc = make_map_2d(&tq, q, (uint64_t)q_rows, (uint64_t)q_width, (uint64_t)ldq, 128, "wm_attn_flash(q)")) return rc;
-  if (int rc = make_map_2d(&tk, k, (uint64_t)k_rows, (uint64_t)k_width, (uint64_t)ldk, 128, "wm_attn_flash(k)")) return rc;
-  if (int rc = make_map_2d(&tv, v, (uint64_t)v_rows, (uint64_t)v_width, (uint64_t)ldv, 128, "wm_attn_flash(v)")) return rc;
+  if (int rc = make_map_2d(&tk, k, (uint64_t)k_rows, (uint64_t)k_width, (uint64_t)ldk, kv_box, "wm_attn_flash(k)")) return rc;
+  if (int rc = make_map_2d(&tv, v, (uint64_t)v_rows, (uint64_t)v_width, (uint64_t)ldv, kv_box, "wm_attn_flash(v)")) return rc;
   trel = tq;
   if (rel_table != nullptr) {
     if (hd != 64 || Tq != 4096 || Tk != 4096) return fail(WM_ERR_SHAPE, "wm_attn_flash: rel-pos needs hd=64, 64x64 tokens");
-    if (int rc = make_map_2d(&trel, rel_table, 256, 64, 64, 256, "wm_attn_flash(rel)")) return rc;
+    if (int rc = make_map_2d(&trel, rel_table, 256, 64, 64, v2 ? 16 : 256, "wm_attn_flash(rel)")) return rc;
   }
   wm::FlashParams p{};
   p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.scale = scale;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldo = (int)ldo;
   p.use_relpos = rel_table != nullptr;
+  if (v2) return check_launch(wm::flash2_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v2)");
   return check_launch(wm::flash_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash");
 }
 

@@ -43,6 +43,9 @@ struct FlashParams {
 int flash_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                    const FlashParams& p, int hd, cudaStream_t st);
 
+int flash2_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
+                    const FlashParams& p, int hd, cudaStream_t st);
+
 struct WindowParams {
   int B, H;     // images, heads
   float scale;

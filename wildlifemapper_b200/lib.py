@@ -19,6 +19,7 @@ SIGNATURES = {
     "wm_version": [],
     "wm_last_error": [],
     "wm_device_check": [],
+    "wm_set_flash_version": [_i],
     "wm_gemm_bf16": [_p, _i64, _p, _i64, _p, _p, _i64, _i, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _p],
     "wm_conv3x3_nhwc_bf16": [_p, _p, _p, _p, _i, _i, _i, _p],
     "wm_layernorm": [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _f, _p],

@@ -42,6 +42,8 @@ int wm_device_check(void);
 /* Select the flash-attention kernel generation used by wm_attn_flash: 2 (default; two query tiles per CTA, O in
  * TMEM, lazy rescaling) or 1 (first-generation kernel, kept for A/B measurements and Tq % 256 != 0). */
 int wm_set_flash_version(int version);
+/* Tuning knobs (for A/B measurements): "flash_version" (1|2|3). */
+int wm_set_option(const char* name, int value);
 
 /* C[M,N] = act(A[M,K] * W[N,K]^T + bias) + residual[(m % res_mod), :]      (tcgen05 / TMEM / TMA)
  * Replaces every nn.Linear / 1x1 Conv2d / patch-embed Conv2d(k16,s16) on the path:

@@ -178,6 +178,25 @@ def test_attn_flash_plain(hd, H, T, flash_version):
     assert (out.float() - ref).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("hd", [64, 128])
+def test_attn_flash_rising_maxima(hd, flash_version):
+    """Scores that keep growing along the key axis force the lazy-rescale path (reference maximum raised, O and l
+    rescaled in TMEM) many times per row, including late key tiles; the two query tiles of a CTA see different
+    score ranges, so the two softmax warpgroups drift apart in time."""
+    B, H, T = 1, 2, 1024
+    q = rnd(B * T, H * hd, seed=40, scale=2.0)
+    kv = rnd(B * T, 2 * H * hd, seed=41)
+    ramp = torch.linspace(0.2, 4.0, T, device=DEV)[:, None]
+    kv[:, :H * hd] = (kv[:, :H * hd].float() * ramp).to(torch.bfloat16)
+    q[T // 4: T // 2] = (q[T // 4: T // 2].float() * 0.05).to(torch.bfloat16)  # a flat-score query tile next to a peaky one
+    out = torch.zeros(B * T, H * hd, device=DEV, dtype=torch.bfloat16)
+    scale = 1 / math.sqrt(hd)
+    ops.attn_flash(q, 0, kv, 0, kv, H * hd, None, out, B, H, T, T, hd, scale)
+    sp = lambda t: t.reshape(B, T, H, hd).transpose(1, 2)
+    ref = ref_attention(sp(q), sp(kv[:, :H * hd]), sp(kv[:, H * hd:]), scale).transpose(1, 2).reshape(B * T, H * hd)
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
 @pytest.fixture(params=[2, 1])
 def flash_version(request):
     """Both flash-attention kernel generations stay parity-checked (2 = default)."""

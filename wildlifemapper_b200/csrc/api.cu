@@ -132,6 +132,12 @@ extern "C" {
 int wm_version(void) { return 100; }
 const char* wm_last_error(void) { return g_err.c_str(); }
 int wm_device_check(void) { return ensure_device(); }
+int wm_set_flash_version(int version);
+int wm_set_option(const char* name, int value) {
+  const std::string n(name ? name : "");
+  if (n == "flash_version") return wm_set_flash_version(value);
+  return fail(WM_ERR_SHAPE, "wm_set_option: unknown option '%s'", n.c_str());
+}
 int wm_set_flash_version(int version) {
   if (version != 1 && version != 2) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 1 or 2");
   g_flash_version = version;

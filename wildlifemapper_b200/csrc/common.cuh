@@ -13,6 +13,19 @@
 #define WM_WAIT_TIMEOUT_NS 2000000000ull
 #endif
 
+#ifdef WM_DEBUG_WAIT
+#include <cstdio>
+// debug build (csrc/build.sh with WM_NVCC_EXTRA=-DWM_DEBUG_WAIT): say which barrier timed out before trapping
+#define WM_WAIT_TRAP(bar, parity)                                                                                     \
+  do {                                                                                                                \
+    printf("wm: mbarrier timeout block (%d,%d,%d) thread %d barrier@%u parity %u\n", (int)blockIdx.x, (int)blockIdx.y, \
+           (int)blockIdx.z, (int)threadIdx.x, smem_u32(bar), (unsigned)(parity));                                     \
+    __trap();                                                                                                         \
+  } while (0)
+#else
+#define WM_WAIT_TRAP(bar, parity) __trap()
+#endif
+
 namespace wm {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,7 +74,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 0x3FFu) == 0) {
       uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > WM_WAIT_TIMEOUT_NS) __trap();
+      else if (now - t0 > WM_WAIT_TIMEOUT_NS) WM_WAIT_TRAP(bar, parity);
     }
   }
 }
@@ -83,7 +96,7 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
     if ((++spins & 0x3Fu) == 0) {
       uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > WM_WAIT_TIMEOUT_NS) __trap();
+      else if (now - t0 > WM_WAIT_TIMEOUT_NS) WM_WAIT_TRAP(bar, parity);
     }
   }
 }

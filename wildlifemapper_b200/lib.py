@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwm_b200.so")
+# WM_LIB_NAME selects an alternative in-tree build (e.g. the -DWM_DEBUG_WAIT diagnostics build)
+LIB_PATH = os.path.join(_HERE, os.environ.get("WM_LIB_NAME", "libwm_b200.so"))
 
 WM_ACT = {"none": 0, "gelu": 1, "relu": 2, "sigmoid": 3}
 
@@ -20,6 +21,7 @@ SIGNATURES = {
     "wm_last_error": [],
     "wm_device_check": [],
     "wm_set_flash_version": [_i],
+    "wm_set_option": [C.c_char_p, _i],
     "wm_gemm_bf16": [_p, _i64, _p, _i64, _p, _p, _i64, _i, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _p],
     "wm_conv3x3_nhwc_bf16": [_p, _p, _p, _p, _i, _i, _i, _p],
     "wm_layernorm": [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _f, _p],
@@ -59,6 +61,9 @@ def load() -> C.CDLL:
         fn.argtypes = argtypes
         fn.restype = C.c_char_p if name == "wm_last_error" else C.c_int
     _lib = lib
+    for env, opt in (("WM_FLASH_VERSION", b"flash_version"),):
+        if os.environ.get(env):  # measurement knobs, see include/wm_b200.h
+            lib.wm_set_option(opt, int(os.environ[env]))
     return lib
 
 

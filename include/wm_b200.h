@@ -39,8 +39,9 @@ int wm_version(void);
 const char* wm_last_error(void);
 /* 0 if the current device is sm_100 and the driver exposes cuTensorMapEncodeTiled */
 int wm_device_check(void);
-/* Select the flash-attention kernel generation used by wm_attn_flash: 2 (default; two query tiles per CTA, O in
- * TMEM, lazy rescaling) or 1 (first-generation kernel, kept for A/B measurements and Tq % 256 != 0). */
+/* Select the flash-attention kernel generation used by wm_attn_flash: 3 (default; 128-key tiles, P kept in tensor
+ * memory, two ping-ponging query tiles per CTA), 2 (64-key tiles, P staged in shared memory) or 1 (first-generation
+ * kernel; also the path taken when Tq % 256 != 0).  Kept selectable for A/B measurements. */
 int wm_set_flash_version(int version);
 /* Tuning knobs (for A/B measurements): "flash_version" (1|2|3). */
 int wm_set_option(const char* name, int value);

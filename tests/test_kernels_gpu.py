@@ -197,13 +197,13 @@ def test_attn_flash_rising_maxima(hd, flash_version):
     assert (out.float() - ref).abs().max().item() < 3e-2
 
 
-@pytest.fixture(params=[2, 1])
+@pytest.fixture(params=[3, 2, 1])
 def flash_version(request):
-    """Both flash-attention kernel generations stay parity-checked (2 = default)."""
+    """All flash-attention kernel generations stay parity-checked (3 = default)."""
     from wildlifemapper_b200 import lib
     lib.call("wm_set_flash_version", request.param)
     yield request.param
-    lib.call("wm_set_flash_version", 2)
+    lib.call("wm_set_flash_version", 3)
 
 
 def relpos_bias(q, rel_h, rel_w, S):

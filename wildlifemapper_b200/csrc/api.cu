@@ -121,7 +121,7 @@ int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, u
   return make_map(m, ptr, 2, dims, strides, box, what);
 }
 
-int g_flash_version = 2;
+int g_flash_version = 3;
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -139,7 +139,7 @@ int wm_set_option(const char* name, int value) {
   return fail(WM_ERR_SHAPE, "wm_set_option: unknown option '%s'", n.c_str());
 }
 int wm_set_flash_version(int version) {
-  if (version != 1 && version != 2) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 1 or 2");
+  if (version < 1 || version > 3) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 1, 2 or 3");
   g_flash_version = version;
   return WM_OK;
 }
@@ -248,6 +248,7 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   if (q_col0 + H * hd > q_width || k_col0 + H * hd > k_width || v_col0 + H * hd > v_width) return fail(WM_ERR_SHAPE, "wm_attn_flash: columns");
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || !aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_attn_flash: alignment");
   if (B > 65535 || H > 65535) return fail(WM_ERR_SHAPE, "wm_attn_flash: grid too large");
+  const bool v3 = (g_flash_version == 3) && (Tq % 256 == 0);
   const bool v2 = (g_flash_version == 2) && (Tq % 256 == 0);
   const uint32_t kv_box = v2 ? 64 : 128;
   CUtensorMap tq, tk, tv, trel;
@@ -257,13 +258,14 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   trel = tq;
   if (rel_table != nullptr) {
     if (hd != 64 || Tq != 4096 || Tk != 4096) return fail(WM_ERR_SHAPE, "wm_attn_flash: rel-pos needs hd=64, 64x64 tokens");
-    if (int rc = make_map_2d(&trel, rel_table, 256, 64, 64, v2 ? 16 : 256, "wm_attn_flash(rel)")) return rc;
+    if (int rc = make_map_2d(&trel, rel_table, 256, 64, 64, (v2 || v3) ? 16 : 256, "wm_attn_flash(rel)")) return rc;
   }
   wm::FlashParams p{};
   p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.scale = scale;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldo = (int)ldo;
   p.use_relpos = rel_table != nullptr;
+  if (v3) return check_launch(wm::flash3_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v3)");
   if (v2) return check_launch(wm::flash2_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v2)");
   return check_launch(wm::flash_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash");
 }

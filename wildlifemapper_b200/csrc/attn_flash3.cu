@@ -1,0 +1,425 @@
+// Flash attention v3 on tcgen05 / TMEM (sm_100a): global 64x64 attention with decomposed rel-pos bias and the
+// HFC cross-attention.  Same math and reference sites as attn_flash.cu (image_encoder.py:246-262, 347-383,
+// 500-503).  Restructured around what the v2 profiles showed (profiles/r01b_*, r01c_*): with 64-key tiles and
+// P staged in shared memory, the 128 x 64 x 16 MMAs re-read their A operand from shared memory every step and
+// the kernel ran out of shared-memory bandwidth (operand reads + P stores + TMA fills ~1.4-1.8k cycles per key
+// tile against ~1.0k cycles of MUFU work), and the softmax warps spent ~45 % of their time waiting for S.
+//
+//   * one CTA = TWO 128-query tiles of one (image, head); key tiles of 128 (two key rows of the 64x64 grid);
+//   * P never touches shared memory: each softmax thread holds its whole 128-score row in registers, and writes
+//     the bf16 probabilities back into the first 64 TMEM columns of its own S tile (tcgen05.st); the P V MMA
+//     reads its A operand from TENSOR MEMORY (tcgen05.mma "ts" form) -- shared memory carries only Q, K, V;
+//   * the two query tiles ping-pong: while the 4 softmax warps of one tile run exp2 on the MUFU, the tensor core
+//     runs P V and the next S of the other tile;
+//   * O accumulates in TMEM across key tiles with LAZY rescaling (reference maximum only raised -- and O, l
+//     rescaled through tcgen05.ld / tcgen05.st -- when a tile exceeds it by more than 2^8); row sums in fp32
+//     registers;
+//   * rel-pos: T_w = Q Rw^T and T_h = Q Rh_slice^T are computed once per CTA by the tensor core; bias_w[64] lives
+//     in registers, T_h stays resident in the spare TMEM columns (one 32-bit read per key row and tile);
+//   * register budget: setmaxnreg moves registers from the producer / MMA warpgroup (40) to the softmax
+//     warpgroups (232).
+//
+//   warp 0       TMA producer (Q tiles, tables, K and V rings)
+//   warp 1       tcgen05.mma issuer          warp 2  TMEM allocator
+//   warps 4-7    softmax of query tile 0     warps 8-11  softmax of query tile 1 (thread = one query row)
+#include "common.cuh"
+#include "wm_internal.h"
+
+namespace wm {
+
+constexpr int F3_THREADS = 384;
+constexpr float F3_LOG2E = 1.4426950408889634f;
+constexpr float F3_TAU = 8.0f;  // lazy-rescale threshold (log2 units): p <= 2^8 between rescales
+
+template <int HD, bool RELPOS>
+struct Flash3Cfg {
+  static_assert(HD % 16 == 0 && HD >= 64 && HD <= 128, "head dim");
+  static_assert(!RELPOS || HD == 64, "rel-pos variant: head dim 64");
+  static constexpr int SUB = (HD + 63) / 64;       // 64-column (128-byte) sub-tiles per operand row
+  static constexpr int KSTEPS = HD / 16;           // K = 16 MMA steps over the head dim
+  static constexpr int STAGES = (SUB == 1) ? 4 : 2;
+  static constexpr int TILE_BYTES = SUB * 16384;   // 128 rows (queries or keys) x SUB x 128 B
+  static constexpr int OFF_Q = 0;                  // 2 query tiles
+  static constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + STAGES * TILE_BYTES;
+  static constexpr int OFF_TAB = OFF_V + STAGES * TILE_BYTES;
+  // RELPOS prologue: Rw [128 rows] + 2 x Rh slice [80 rows]; afterwards the first 32 KB are fp32 scatter scratch
+  static constexpr int TAB_BYTES = RELPOS ? (16384 + 2 * 10240) : 0;
+  static constexpr int OFF_BAR = OFF_TAB + TAB_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  // TMEM columns: S_t at 128 t (P_t = bf16 pairs in its first 64 columns), O_t at 256 + HD t,
+  // RELPOS: T_h(t) columns 0..63 at 384 + 64 t (resident), prologue scratch in the S / O columns
+  static constexpr int COL_O = 256;
+  static constexpr int COL_TH = 384;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(COL_O + 2 * HD <= (RELPOS ? COL_TH : 512), "TMEM budget");
+};
+
+template <int HD, bool RELPOS>
+__global__ void __launch_bounds__(F3_THREADS, 1)
+flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_rel,
+              const FlashParams p) {
+  using Cfg = Flash3Cfg<HD, RELPOS>;
+  constexpr int NS = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [4]
+  uint64_t* k_empty = bars + 5;   // [4]
+  uint64_t* v_full = bars + 9;    // [4]
+  uint64_t* v_empty = bars + 13;  // [4]
+  uint64_t* s_full = bars + 17;   // [2]  S_t(j) complete (implies P_t(j-1) V has completed: in-order tensor pipe)
+  uint64_t* p_full = bars + 19;   // [2]  P_t(j) stored to TMEM by the 4 warps of tile t
+  uint64_t* o_full = bars + 21;   // [2]
+  uint64_t* t_full = bars + 23;   // rel-pos table products complete
+  uint64_t* t_done = bars + 24;   // ... and drained out of the S / O columns by the 8 softmax warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int nk = p.Tk / 128;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+    }
+    mbar_init(t_full, 1);
+    mbar_init(t_done, 8);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    setmaxnreg_dec<40>();
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES + Cfg::TAB_BYTES);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int s = 0; s < Cfg::SUB; ++s)
+          tma_load_2d(smem + Cfg::OFF_Q + t * Cfg::TILE_BYTES + s * 16384, &tmap_q, q_full, p.q_col0 + h * HD + s * 64,
+                      b * p.Tq + m0 + t * 128);
+      if (RELPOS) {
+        // table tensor [256,64]: rows 0..126 rel_pos_h, 128..254 rel_pos_w.  Box = 16 rows.
+        const int qi0 = m0 >> 6;  // first image row of this CTA (4 rows: 2 per query tile)
+        for (int i = 0; i < 8; ++i) tma_load_2d(smem + Cfg::OFF_TAB + i * 2048, &tmap_rel, q_full, 0, 128 + 16 * i);
+        for (int t = 0; t < 2; ++t)
+          for (int i = 0; i < 5; ++i)
+            tma_load_2d(smem + Cfg::OFF_TAB + 16384 + t * 10240 + i * 2048, &tmap_rel, q_full, 0, qi0 + 2 * t + 16 * i);
+      }
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nk; ++j) {
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int s = 0; s < Cfg::SUB; ++s)
+          tma_load_2d(smem + Cfg::OFF_K + st * Cfg::TILE_BYTES + s * 16384, &tmap_k, &k_full[st],
+                      p.k_col0 + h * HD + s * 64, b * p.Tk + j * 128);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int s = 0; s < Cfg::SUB; ++s)
+          tma_load_2d(smem + Cfg::OFF_V + st * Cfg::TILE_BYTES + s * 16384, &tmap_v, &v_full[st],
+                      p.v_col0 + h * HD + s * 64, b * p.Tk + j * 128);
+        if (++st == NS) { st = 0; ph ^= 1; }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);  // A = P from TMEM (K-major), V is MN-major
+      const uint32_t sq = smem_u32(smem + Cfg::OFF_Q);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      if (RELPOS) {
+        constexpr uint32_t idesc_tw = make_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc_th = make_idesc_bf16(128, 64, 0, 0);
+        constexpr uint32_t idesc_tx = make_idesc_bf16(128, 16, 0, 0);
+        const uint32_t stab = smem_u32(smem + Cfg::OFF_TAB);
+        // T_w(t) -> S_t columns; T_h(t)[0..63] -> resident columns; T_h(t)[64..79] -> scratch in the O columns
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t srh = stab + 16384 + t * 10240;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES + ks * 32, 16, 1024);
+            umma_bf16(tmem_base + t * 128, ad, make_sdesc_sw128(stab + ks * 32, 16, 1024), idesc_tw, ks != 0);
+            umma_bf16(tmem_base + Cfg::COL_TH + t * 64, ad, make_sdesc_sw128(srh + ks * 32, 16, 1024), idesc_th, ks != 0);
+            umma_bf16(tmem_base + Cfg::COL_O + t * 16, ad, make_sdesc_sw128(srh + 8192 + ks * 32, 16, 1024), idesc_tx,
+                      ks != 0);
+          }
+        }
+        umma_commit(t_full);
+        mbar_wait(t_done, 0);  // both warpgroups have drained the scratch out of the S / O columns
+        tc_fence_after();
+      }
+      // (loops over MMA steps are deliberately not unrolled: this warpgroup runs on 40 registers)
+      auto issue_s = [&](int t, int st) {
+        const uint64_t qd = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES, 16, 1024);
+        const uint64_t kd = make_sdesc_sw128(smem_u32(smem + Cfg::OFF_K + st * Cfg::TILE_BYTES), 16, 1024);
+#pragma unroll 1
+        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+          const uint32_t off = (uint32_t)((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);  // descriptor address field is bytes >> 4
+          umma_bf16(tmem_base + t * 128, qd + off, kd + off, idesc_s, ks != 0);
+        }
+        umma_commit(&s_full[t]);
+      };
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      umma_commit(&k_empty[0]);
+      int st = 0;         // V stage of tile j
+      uint32_t ph = 0;
+      for (int j = 0; j < nk; ++j) {
+        const bool more = j + 1 < nk;
+        int kst = st + 1;  // K stage of tile j + 1
+        uint32_t kph = ph;
+        if (kst == NS) { kst = 0; kph ^= 1; }
+        const uint32_t sv = smem_u32(smem + Cfg::OFF_V + st * Cfg::TILE_BYTES);
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_full[t], j & 1);
+          if (t == 0) mbar_wait(&v_full[st], ph);
+          tc_fence_after();
+          const uint64_t vd = make_sdesc_sw128(sv, 16384, 1024);
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks)  // 128 keys, 16 per MMA; P_t: 8 TMEM columns per step; V: 2048 B per step
+            umma_bf16_ts(tmem_base + Cfg::COL_O + t * HD, tmem_base + t * 128 + ks * 8, vd + (uint32_t)(ks * (2048 >> 4)),
+                         idesc_pv, (j | ks) != 0);
+          if (more) {
+            if (t == 0) {
+              mbar_wait(&k_full[kst], kph);
+              tc_fence_after();
+            }
+            issue_s(t, kst);  // overwrites S_t / P_t: ordered behind the P V MMAs above
+          } else {
+            umma_commit(&o_full[t]);
+          }
+        }
+        umma_commit(&v_empty[st]);
+        if (more) umma_commit(&k_empty[kst]);
+        if (++st == NS) { st = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax / correction / output
+    setmaxnreg_inc<232>();
+    const int t = (warp - 4) >> 2;  // query tile of this warpgroup
+    const int q4 = warp & 3;        // TMEM lane quarter
+    const int r = q4 * 32 + lane;   // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const uint32_t s_addr = lane_addr + t * 128;
+    const uint32_t o_addr = lane_addr + Cfg::COL_O + t * HD;
+    const float c1 = p.scale * F3_LOG2E;
+    float tw[RELPOS ? 64 : 1];
+    float bh64 = 0.0f;                                            // T_h column 64 (only needed by key row 0)
+    const int hi = r >> 6;                                        // image row of this query inside the tile (warp-uniform)
+    const uint32_t th_addr = lane_addr + Cfg::COL_TH + t * 64;    // bias_h[kh] = T_h[hi + 63 - kh]
+
+    if (RELPOS) {
+      const int qj = (m0 + t * 128 + r) & 63;
+      mbar_wait(t_full, 0);
+      tc_fence_after();
+      {
+        const uint32_t x = tmem_ld1(lane_addr + Cfg::COL_O + t * 16);
+        tmem_ld_wait();
+        bh64 = __uint_as_float(x) * F3_LOG2E;
+      }
+      // bias_w[kw] = T_w[qj + 63 - kw]: per-thread scatter through a private XOR-swizzled 32-float smem row
+      float* scr = reinterpret_cast<float*>(smem + Cfg::OFF_TAB) + ((t * 128 + r) << 5);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(s_addr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kw = qj + 63 - (c * 32 + i) - half * 32;
+            if (kw >= 0 && kw < 32) scr[((((kw >> 2) ^ (r & 7)) << 2) | (kw & 3))] = __uint_as_float(v[i]) * F3_LOG2E;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 w = *reinterpret_cast<const float4*>(scr + ((g ^ (r & 7)) << 2));
+          tw[half * 32 + 4 * g] = w.x; tw[half * 32 + 4 * g + 1] = w.y;
+          tw[half * 32 + 4 * g + 2] = w.z; tw[half * 32 + 4 * g + 3] = w.w;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_done);
+    }
+
+    float m_ref = -INFINITY, l_run = 0.0f;
+    for (int j = 0; j < nk; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      float y[128];
+      {
+        uint32_t(&v)[128] = reinterpret_cast<uint32_t(&)[128]>(y);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
+      }
+      float bh0 = 0.0f, bh1 = 0.0f;
+      if (RELPOS) {
+        const int c0 = hi + 63 - 2 * j;  // column of key row 2j; key row 2j+1 is column c0 - 1 (>= 0)
+        const uint32_t a0 = tmem_ld1(th_addr + (c0 > 63 ? 63 : c0));
+        const uint32_t a1 = tmem_ld1(th_addr + c0 - 1);
+        tmem_ld_wait();
+        bh0 = (c0 > 63) ? bh64 : __uint_as_float(a0) * F3_LOG2E;
+        bh1 = __uint_as_float(a1) * F3_LOG2E;
+      } else {
+        tmem_ld_wait();
+      }
+      // ---- scores in the exp2 domain and their row maximum
+      float m_tile;
+      if (RELPOS) {
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          y[i] = fmaf(y[i], c1, tw[RELPOS ? i : 0]);
+          mx0 = fmaxf(mx0, y[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          y[64 + i] = fmaf(y[64 + i], c1, tw[RELPOS ? i : 0]);
+          mx1 = fmaxf(mx1, y[64 + i]);
+        }
+        m_tile = fmaxf(mx0 + bh0, mx1 + bh1);
+      } else {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, y[i]);
+        m_tile = mx * c1;  // c1 > 0
+      }
+      const bool need = m_tile > m_ref + F3_TAU;  // always true for the first tile (m_ref = -inf)
+      if (__any_sync(0xffffffffu, need)) {
+        // ---- raise the reference maximum; rescale O and l (warp-collective TMEM traffic).  s_full(j) implies that
+        // P(j-1) V has completed, so O is stable here.
+        const float m_new = need ? m_tile : m_ref;
+        if (j > 0) {
+          const float alpha = ex2_approx(m_ref - m_new);  // 1 for lanes that did not need it
+#pragma unroll
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(o_addr + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(o_addr + c * 16, o);
+          }
+          l_run *= alpha;
+        }
+        m_ref = m_new;
+      }
+      // ---- probabilities: bf16 pairs back into the first 64 columns of this tile's S (the P V A operand)
+      float lsum = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+        if (RELPOS) {
+          const float d = ((c < 2) ? bh0 : bh1) - m_ref;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e0 = ex2_approx(y[c * 32 + 2 * i] + d), e1 = ex2_approx(y[c * 32 + 2 * i + 1] + d);
+            lsum += e0 + e1;
+            pk[i] = pack_bf16(e0, e1);
+          }
+        } else {
+          const float d = -m_ref;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e0 = ex2_approx(fmaf(y[c * 32 + 2 * i], c1, d)), e1 = ex2_approx(fmaf(y[c * 32 + 2 * i + 1], c1, d));
+            lsum += e0 + e1;
+            pk[i] = pack_bf16(e0, e1);
+          }
+        }
+        tmem_st16(s_addr + c * 16, pk);
+      }
+      l_run += lsum;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+    // ---- epilogue: O / l
+    mbar_wait(&o_full[t], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    __nv_bfloat16* dst = p.out + (size_t)(b * p.Tq + m0 + t * 128 + r) * p.ldo + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld16(o_addr + c * 16, o);
+      tmem_ld_wait();
+      uint4* d4 = reinterpret_cast<uint4*>(dst + c * 16);
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        d4[g] = make_uint4(pack_bf16(__uint_as_float(o[8 * g]) * inv_l, __uint_as_float(o[8 * g + 1]) * inv_l),
+                           pack_bf16(__uint_as_float(o[8 * g + 2]) * inv_l, __uint_as_float(o[8 * g + 3]) * inv_l),
+                           pack_bf16(__uint_as_float(o[8 * g + 4]) * inv_l, __uint_as_float(o[8 * g + 5]) * inv_l),
+                           pack_bf16(__uint_as_float(o[8 * g + 6]) * inv_l, __uint_as_float(o[8 * g + 7]) * inv_l));
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int HD, bool RELPOS>
+static int launch_flash3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
+                         const FlashParams& p, cudaStream_t st) {
+  using Cfg = Flash3Cfg<HD, RELPOS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(flash3_kernel<HD, RELPOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+        cudaSuccess)
+      return WM_ERR_CUDA;
+    attr_set = true;
+  }
+  dim3 grid(p.Tq / 256, p.H, p.B);
+  flash3_kernel<HD, RELPOS><<<grid, F3_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, trel, p);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// q tiles: box 128 rows; k/v tiles: box 128 rows; rel table [256,64]: box 16 rows
+int flash3_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
+                    const FlashParams& p, int hd, cudaStream_t st) {
+  if (p.Tq % 256 != 0 || p.Tk % 128 != 0 || p.Tk < 128) return WM_ERR_SHAPE;
+  if (p.use_relpos) {
+    if (hd != 64 || p.Tq != 4096 || p.Tk != 4096) return WM_ERR_SHAPE;
+    return launch_flash3<64, true>(tq, tk, tv, trel, p, st);
+  }
+  if (hd == 64) return launch_flash3<64, false>(tq, tk, tv, trel, p, st);
+  if (hd == 128) return launch_flash3<128, false>(tq, tk, tv, trel, p, st);
+  return WM_ERR_SHAPE;
+}
+
+}  // namespace wm

@@ -45,6 +45,8 @@ int flash_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
 
 int flash2_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                     const FlashParams& p, int hd, cudaStream_t st);
+int flash3_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
+                    const FlashParams& p, int hd, cudaStream_t st);
 
 struct WindowParams {
   int B, H;     // images, heads

@@ -43,8 +43,12 @@ int wm_device_check(void);
  * memory, two ping-ponging query tiles per CTA), 2 (64-key tiles, P staged in shared memory) or 1 (first-generation
  * kernel; also the path taken when Tq % 256 != 0).  Kept selectable for A/B measurements. */
 int wm_set_flash_version(int version);
-/* Tuning knobs (for A/B measurements): "flash_version" (1|2|3). */
+/* Tuning knobs (for A/B measurements): "flash_version" (1|2|3), "flash_turns" (0|1: v3 softmax warpgroups take turns
+ * on the MUFU). */
 int wm_set_option(const char* name, int value);
+/* Diagnostics build only (csrc/build.sh with -DWM_F3_TRACE): copy the SM-clock event trace of CTA (0,0,0) of the last
+ * v3 flash-attention launch to host_out[3][64][4]; returns WM_ERR_ARCH in the product build. */
+int wm_debug_flash_trace(uint64_t* host_out_3x64x4);
 
 /* C[M,N] = act(A[M,K] * W[N,K]^T + bias) + residual[(m % res_mod), :]      (tcgen05 / TMEM / TMA)
  * Replaces every nn.Linear / 1x1 Conv2d / patch-embed Conv2d(k16,s16) on the path:

@@ -1,0 +1,109 @@
+// Microbenchmark (B200): how fast can 1 or 2 warps per SM sub-partition run the softmax inner loop?
+//   variants: 0 MUFU.EX2 only | 1 scalar mix (FADD, MUFU, FADD, FADD, F2FP per pair -- the flash-v3 exp phase)
+//             2 packed mix (add.f32x2 for the shift and the row sum) | 3 polynomial exp2 on the FMA pipe only
+//             4 mix with 25 % of the exponentials on the FMA pipe | 5 FMNMX max phase (FFMA + FMNMX per score)
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mufu_bench mufu_bench.cu ; run: ./mufu_bench
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack(float a, float b) { __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+// exp2 for x <= 0 on the FMA/ALU pipes: 2^x = 2^floor(x) * p(frac), cubic minimax (FA4-style), rel err ~1e-4
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float fl = floorf(x);   // FRND is a conversion-pipe op on some parts; use the magic-number trick instead
+  (void)fl;
+  const float t = x + 12582912.0f;              // 1.5 * 2^23: round to nearest integer in the mantissa
+  const float n = t - 12582912.0f;
+  const float f = x - n;                        // in [-0.5, 0.5]
+  float p = fmaf(f, 0.0555041f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256, 1) bench(float* out, long long* cycles, int iters, float d) {
+  float y[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) y[i] = -0.01f * (float)((threadIdx.x * 131 + i * 7) & 255);
+  float acc[4] = {0, 0, 0, 0};
+  uint32_t pk = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (VARIANT == 0) {
+#pragma unroll
+      for (int i = 0; i < 128; ++i) acc[i & 3] += ex2(y[i]);
+    } else if (VARIANT == 1) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float e0 = ex2(y[2 * i] + d), e1 = ex2(y[2 * i + 1] + d);
+        acc[i & 3] += e0 + e1;
+        pk ^= pack(e0, e1);
+      }
+    } else if (VARIANT == 2) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        float2 s;
+        asm("{.reg .b64 a, b, c; mov.b64 a, {%2, %3}; mov.b64 b, {%4, %4}; add.f32x2 c, a, b; mov.b64 {%0, %1}, c;}"
+            : "=f"(s.x), "=f"(s.y) : "f"(y[2 * i]), "f"(y[2 * i + 1]), "f"(d));
+        const float e0 = ex2(s.x), e1 = ex2(s.y);
+        asm("{.reg .b64 a, b, c; mov.b64 a, {%0, %1}; mov.b64 b, {%2, %3}; add.f32x2 c, a, b; mov.b64 {%0, %1}, c;}"
+            : "+f"(acc[0]), "+f"(acc[1]) : "f"(e0), "f"(e1));
+        pk ^= pack(e0, e1);
+      }
+    } else if (VARIANT == 3) {
+#pragma unroll
+      for (int i = 0; i < 128; ++i) acc[i & 3] += ex2_poly(y[i] + d);
+    } else if (VARIANT == 4) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float e0 = ex2(y[2 * i] + d);
+        const float e1 = (i & 1) ? ex2(y[2 * i + 1] + d) : ex2_poly(y[2 * i + 1] + d);
+        acc[i & 3] += e0 + e1;
+        pk ^= pack(e0, e1);
+      }
+    } else if (VARIANT == 5) {
+#pragma unroll
+      for (int i = 0; i < 128; ++i) {
+        y[i] = fmaf(y[i], 1.0001f, d);
+        acc[i & 3] = fmaxf(acc[i & 3], y[i]);
+      }
+    }
+    d += acc[0] * 1e-30f;
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc[0] + acc[1] + acc[2] + acc[3] + __uint_as_float(pk) + y[5];
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int V>
+void run(const char* name, int warps_per_smsp) {
+  const int threads = 128 * warps_per_smsp, iters = 200;
+  float* out; long long* cyc;
+  cudaMalloc(&out, 148 * 256 * 4); cudaMalloc(&cyc, 148 * 8);
+  bench<V><<<148, threads>>>(out, cyc, iters, -0.5f);
+  cudaDeviceSynchronize();
+  bench<V><<<148, threads>>>(out, cyc, iters, -0.5f);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h[148]; cudaMemcpy(h, cyc, 148 * 8, cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
+  printf("%-34s %d warp/SMSP: %8.1f cycles per 128-score tile per warp-slot (%.2f cycles per score per SMSP)  %s\n", name, warps_per_smsp,
+         avg / iters, avg / iters / 128.0 / warps_per_smsp * 1.0, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+  for (int w = 1; w <= 2; ++w) {
+    run<0>("MUFU.EX2 only", w);
+    run<1>("scalar mix (v3 exp phase)", w);
+    run<2>("packed f32x2 mix", w);
+    run<3>("polynomial exp2 (FMA pipe)", w);
+    run<4>("mix, 25% polynomial", w);
+    run<5>("max phase (FFMA + FMNMX)", w);
+  }
+  return 0;
+}

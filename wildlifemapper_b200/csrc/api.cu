@@ -122,6 +122,7 @@ int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, u
 }
 
 int g_flash_version = 3;
+int g_flash_turns = 1;
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -136,6 +137,7 @@ int wm_set_flash_version(int version);
 int wm_set_option(const char* name, int value) {
   const std::string n(name ? name : "");
   if (n == "flash_version") return wm_set_flash_version(value);
+  if (n == "flash_turns") { g_flash_turns = value != 0; return WM_OK; }
   return fail(WM_ERR_SHAPE, "wm_set_option: unknown option '%s'", n.c_str());
 }
 int wm_set_flash_version(int version) {
@@ -265,9 +267,16 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldo = (int)ldo;
   p.use_relpos = rel_table != nullptr;
+  p.turns = g_flash_turns;
   if (v3) return check_launch(wm::flash3_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v3)");
   if (v2) return check_launch(wm::flash2_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v2)");
   return check_launch(wm::flash_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash");
+}
+
+int wm_debug_flash_trace(uint64_t* host_out_3x64x4) {
+  if (wm::flash3_read_trace(reinterpret_cast<unsigned long long*>(host_out_3x64x4)) != WM_OK)
+    return fail(WM_ERR_ARCH, "wm_debug_flash_trace: only available in the diagnostics build (-DWM_F3_TRACE)");
+  return WM_OK;
 }
 
 int wm_attn_window(const void* qkv, const void* rel_table, void* out_bf16, int B, int H, int D, float scale,

@@ -31,6 +31,20 @@ constexpr int F3_THREADS = 384;
 constexpr float F3_LOG2E = 1.4426950408889634f;
 constexpr float F3_TAU = 8.0f;  // lazy-rescale threshold (log2 units): p <= 2^8 between rescales
 
+#ifdef WM_F3_TRACE
+// Diagnostics build only: per-event SM clock stamps of CTA (0,0,0) -- [role][key tile][event]; role 0/1 = softmax
+// warpgroup of query tile 0/1 (0 S ready, 1 scores loaded, 2 maximum known, 3 turn acquired, 4 all P stores issued,
+// 5 P stores complete), role 2 = MMA issuer (0 P_0 seen, 1 P_0 V issued, 2 S_0 issued, 3 P_1 seen, 4 P_1 V issued,
+// 5 S_1 issued).
+__device__ unsigned long long g_f3_trace[3][64][8];
+#define F3_TRACE(role, j, ev)                                                                   \
+  do {                                                                                          \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64) g_f3_trace[role][j][ev] = clock64(); \
+  } while (0)
+#else
+#define F3_TRACE(role, j, ev) do { } while (0)
+#endif
+
 template <int HD, bool RELPOS>
 struct Flash3Cfg {
   static_assert(HD % 16 == 0 && HD >= 64 && HD <= 128, "head dim");
@@ -56,7 +70,7 @@ struct Flash3Cfg {
   static_assert(COL_O + 2 * HD <= (RELPOS ? COL_TH : 512), "TMEM budget");
 };
 
-template <int HD, bool RELPOS>
+template <int HD, bool RELPOS, bool TURNS>
 __global__ void __launch_bounds__(F3_THREADS, 1)
 flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
               const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_rel,
@@ -78,7 +92,7 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint64_t* t_done = bars + 24;   // ... and drained out of the S / O columns by the 8 softmax warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
   const int nk = p.Tk / 128;
 
@@ -110,44 +124,54 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
   if (warp < 4) {
     setmaxnreg_dec<40>();
-    if (warp == 0 && lane == 0) {
+    // Producer and MMA roles: the WHOLE warp runs the control flow (uniform branches, every lane polls the
+    // barriers); one elected lane issues the TMA / tcgen05 instructions.
+    if (warp == 0) {
       // ------------------------------------------------------------ TMA producer
-      mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES + Cfg::TAB_BYTES);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES + Cfg::TAB_BYTES);
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int s = 0; s < Cfg::SUB; ++s)
-          tma_load_2d(smem + Cfg::OFF_Q + t * Cfg::TILE_BYTES + s * 16384, &tmap_q, q_full, p.q_col0 + h * HD + s * 64,
-                      b * p.Tq + m0 + t * 128);
-      if (RELPOS) {
-        // table tensor [256,64]: rows 0..126 rel_pos_h, 128..254 rel_pos_w.  Box = 16 rows.
-        const int qi0 = m0 >> 6;  // first image row of this CTA (4 rows: 2 per query tile)
-        for (int i = 0; i < 8; ++i) tma_load_2d(smem + Cfg::OFF_TAB + i * 2048, &tmap_rel, q_full, 0, 128 + 16 * i);
         for (int t = 0; t < 2; ++t)
-          for (int i = 0; i < 5; ++i)
-            tma_load_2d(smem + Cfg::OFF_TAB + 16384 + t * 10240 + i * 2048, &tmap_rel, q_full, 0, qi0 + 2 * t + 16 * i);
+#pragma unroll
+          for (int s = 0; s < Cfg::SUB; ++s)
+            tma_load_2d(smem + Cfg::OFF_Q + t * Cfg::TILE_BYTES + s * 16384, &tmap_q, q_full, p.q_col0 + h * HD + s * 64,
+                        b * p.Tq + m0 + t * 128);
+        if (RELPOS) {
+          // table tensor [256,64]: rows 0..126 rel_pos_h, 128..254 rel_pos_w.  Box = 16 rows.
+          const int qi0 = m0 >> 6;  // first image row of this CTA (4 rows: 2 per query tile)
+          for (int i = 0; i < 8; ++i) tma_load_2d(smem + Cfg::OFF_TAB + i * 2048, &tmap_rel, q_full, 0, 128 + 16 * i);
+          for (int t = 0; t < 2; ++t)
+            for (int i = 0; i < 5; ++i)
+              tma_load_2d(smem + Cfg::OFF_TAB + 16384 + t * 10240 + i * 2048, &tmap_rel, q_full, 0, qi0 + 2 * t + 16 * i);
+        }
       }
       int st = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nk; ++j) {
         mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
 #pragma unroll
-        for (int s = 0; s < Cfg::SUB; ++s)
-          tma_load_2d(smem + Cfg::OFF_K + st * Cfg::TILE_BYTES + s * 16384, &tmap_k, &k_full[st],
-                      p.k_col0 + h * HD + s * 64, b * p.Tk + j * 128);
+          for (int s = 0; s < Cfg::SUB; ++s)
+            tma_load_2d(smem + Cfg::OFF_K + st * Cfg::TILE_BYTES + s * 16384, &tmap_k, &k_full[st],
+                        p.k_col0 + h * HD + s * 64, b * p.Tk + j * 128);
+        }
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
 #pragma unroll
-        for (int s = 0; s < Cfg::SUB; ++s)
-          tma_load_2d(smem + Cfg::OFF_V + st * Cfg::TILE_BYTES + s * 16384, &tmap_v, &v_full[st],
-                      p.v_col0 + h * HD + s * 64, b * p.Tk + j * 128);
+          for (int s = 0; s < Cfg::SUB; ++s)
+            tma_load_2d(smem + Cfg::OFF_V + st * Cfg::TILE_BYTES + s * 16384, &tmap_v, &v_full[st],
+                        p.v_col0 + h * HD + s * 64, b * p.Tk + j * 128);
+        }
+        __syncwarp();
         if (++st == NS) { st = 0; ph ^= 1; }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ------------------------------------------------------------ MMA issuer
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);  // A = P from TMEM (K-major), V is MN-major
+      const bool leader = elect_one();  // the same lane issues every tcgen05.mma / tcgen05.commit
       const uint32_t sq = smem_u32(smem + Cfg::OFF_Q);
       mbar_wait(q_full, 0);
       tc_fence_after();
@@ -157,38 +181,44 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         constexpr uint32_t idesc_tx = make_idesc_bf16(128, 16, 0, 0);
         const uint32_t stab = smem_u32(smem + Cfg::OFF_TAB);
         // T_w(t) -> S_t columns; T_h(t)[0..63] -> resident columns; T_h(t)[64..79] -> scratch in the O columns
+        if (leader) {
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const uint32_t srh = stab + 16384 + t * 10240;
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t srh = stab + 16384 + t * 10240;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES + ks * 32, 16, 1024);
-            umma_bf16(tmem_base + t * 128, ad, make_sdesc_sw128(stab + ks * 32, 16, 1024), idesc_tw, ks != 0);
-            umma_bf16(tmem_base + Cfg::COL_TH + t * 64, ad, make_sdesc_sw128(srh + ks * 32, 16, 1024), idesc_th, ks != 0);
-            umma_bf16(tmem_base + Cfg::COL_O + t * 16, ad, make_sdesc_sw128(srh + 8192 + ks * 32, 16, 1024), idesc_tx,
-                      ks != 0);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ad = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES + ks * 32, 16, 1024);
+              umma_bf16(tmem_base + t * 128, ad, make_sdesc_sw128(stab + ks * 32, 16, 1024), idesc_tw, ks != 0);
+              umma_bf16(tmem_base + Cfg::COL_TH + t * 64, ad, make_sdesc_sw128(srh + ks * 32, 16, 1024), idesc_th, ks != 0);
+              umma_bf16(tmem_base + Cfg::COL_O + t * 16, ad, make_sdesc_sw128(srh + 8192 + ks * 32, 16, 1024), idesc_tx,
+                        ks != 0);
+            }
           }
+          umma_commit(t_full);
         }
-        umma_commit(t_full);
+        __syncwarp();
         mbar_wait(t_done, 0);  // both warpgroups have drained the scratch out of the S / O columns
         tc_fence_after();
       }
-      // (loops over MMA steps are deliberately not unrolled: this warpgroup runs on 40 registers)
-      auto issue_s = [&](int t, int st) {
-        const uint64_t qd = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES, 16, 1024);
-        const uint64_t kd = make_sdesc_sw128(smem_u32(smem + Cfg::OFF_K + st * Cfg::TILE_BYTES), 16, 1024);
-#pragma unroll 1
-        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
-          const uint32_t off = (uint32_t)((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);  // descriptor address field is bytes >> 4
-          umma_bf16(tmem_base + t * 128, qd + off, kd + off, idesc_s, ks != 0);
+      auto issue_s = [&](int t, int st) {  // S_t = Q_t K^T into TMEM columns [128 t, 128 t + 128)
+        if (leader) {
+          const uint64_t qd = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES, 16, 1024);
+          const uint64_t kd = make_sdesc_sw128(smem_u32(smem + Cfg::OFF_K + st * Cfg::TILE_BYTES), 16, 1024);
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+            const uint32_t off = (uint32_t)((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);  // address field is bytes >> 4
+            umma_bf16(tmem_base + t * 128, qd + off, kd + off, idesc_s, ks != 0);
+          }
+          umma_commit(&s_full[t]);
         }
-        umma_commit(&s_full[t]);
+        __syncwarp();
       };
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_s(0, 0);
       issue_s(1, 0);
-      umma_commit(&k_empty[0]);
+      if (leader) umma_commit(&k_empty[0]);
+      __syncwarp();
       int st = 0;         // V stage of tile j
       uint32_t ph = 0;
       for (int j = 0; j < nk; ++j) {
@@ -197,28 +227,38 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         uint32_t kph = ph;
         if (kst == NS) { kst = 0; kph ^= 1; }
         const uint32_t sv = smem_u32(smem + Cfg::OFF_V + st * Cfg::TILE_BYTES);
-#pragma unroll 1
+#pragma unroll
         for (int t = 0; t < 2; ++t) {
           mbar_wait(&p_full[t], j & 1);
           if (t == 0) mbar_wait(&v_full[st], ph);
           tc_fence_after();
-          const uint64_t vd = make_sdesc_sw128(sv, 16384, 1024);
-#pragma unroll 1
-          for (int ks = 0; ks < 8; ++ks)  // 128 keys, 16 per MMA; P_t: 8 TMEM columns per step; V: 2048 B per step
-            umma_bf16_ts(tmem_base + Cfg::COL_O + t * HD, tmem_base + t * 128 + ks * 8, vd + (uint32_t)(ks * (2048 >> 4)),
-                         idesc_pv, (j | ks) != 0);
+          if (leader) F3_TRACE(2, j, 3 * t);
+          if (leader) {
+            const uint64_t vd = make_sdesc_sw128(sv, 16384, 1024);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)  // 128 keys, 16 per MMA; P_t: 8 TMEM columns per step; V: 2048 B per step
+              umma_bf16_ts(tmem_base + Cfg::COL_O + t * HD, tmem_base + t * 128 + ks * 8,
+                           vd + (uint32_t)(ks * (2048 >> 4)), idesc_pv, (j | ks) != 0);
+          }
+          if (leader) F3_TRACE(2, j, 3 * t + 1);
+          __syncwarp();
           if (more) {
             if (t == 0) {
               mbar_wait(&k_full[kst], kph);
               tc_fence_after();
             }
             issue_s(t, kst);  // overwrites S_t / P_t: ordered behind the P V MMAs above
+            if (leader) F3_TRACE(2, j, 3 * t + 2);
           } else {
-            umma_commit(&o_full[t]);
+            if (leader) umma_commit(&o_full[t]);
+            __syncwarp();
           }
         }
-        umma_commit(&v_empty[st]);
-        if (more) umma_commit(&k_empty[kst]);
+        if (leader) {
+          umma_commit(&v_empty[st]);
+          if (more) umma_commit(&k_empty[kst]);
+        }
+        __syncwarp();
         if (++st == NS) { st = 0; ph ^= 1; }
       }
     }
@@ -273,16 +313,21 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       if (lane == 0) mbar_arrive(t_done);
     }
 
+    // TURNS: the two warpgroups take turns on the MUFU (named barriers 2 + t) -- tile 0's exp2 phase runs while the
+    // tensor core works on tile 1 and vice versa, instead of both tiles stretching each other's exp2 phase.
+    if (TURNS && t == 1) named_bar_arrive(2, 256);  // tile 0 goes first
     float m_ref = -INFINITY, l_run = 0.0f;
     for (int j = 0; j < nk; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      float y[128];
-      {
-        uint32_t(&v)[128] = reinterpret_cast<uint32_t(&)[128]>(y);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
-      }
+      if (q4 == 0 && lane == 0) F3_TRACE(t, j, 0);
+      // One pass over the 128 scores of this row in four 32-column chunks; the TMEM load of chunk c+1 is in flight
+      // while chunk c is processed.  Each chunk is first evaluated OPTIMISTICALLY against the current reference
+      // maximum; only if some row of the warp exceeds it by more than 2^TAU is the reference raised (O, l and the
+      // chunks of P already written are rescaled) and the chunk recomputed from the registers that still hold it.
+      // P chunk c (16 columns of bf16 pairs) overwrites S columns [16c, 16c+16), which chunk c/2 has already consumed.
+      uint32_t v[2][32];
+      tmem_ld32(s_addr, v[0]);
       float bh0 = 0.0f, bh1 = 0.0f;
       if (RELPOS) {
         const int c0 = hi + 63 - 2 * j;  // column of key row 2j; key row 2j+1 is column c0 - 1 (>= 0)
@@ -294,73 +339,104 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       } else {
         tmem_ld_wait();
       }
-      // ---- scores in the exp2 domain and their row maximum
-      float m_tile;
-      if (RELPOS) {
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          y[i] = fmaf(y[i], c1, tw[RELPOS ? i : 0]);
-          mx0 = fmaxf(mx0, y[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          y[64 + i] = fmaf(y[64 + i], c1, tw[RELPOS ? i : 0]);
-          mx1 = fmaxf(mx1, y[64 + i]);
-        }
-        m_tile = fmaxf(mx0 + bh0, mx1 + bh1);
-      } else {
-        float mx = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, y[i]);
-        m_tile = mx * c1;  // c1 > 0
-      }
-      const bool need = m_tile > m_ref + F3_TAU;  // always true for the first tile (m_ref = -inf)
-      if (__any_sync(0xffffffffu, need)) {
-        // ---- raise the reference maximum; rescale O and l (warp-collective TMEM traffic).  s_full(j) implies that
-        // P(j-1) V has completed, so O is stable here.
-        const float m_new = need ? m_tile : m_ref;
-        if (j > 0) {
-          const float alpha = ex2_approx(m_ref - m_new);  // 1 for lanes that did not need it
-#pragma unroll
-          for (int c = 0; c < HD / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld16(o_addr + c * 16, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(o_addr + c * 16, o);
-          }
-          l_run *= alpha;
-        }
-        m_ref = m_new;
-      }
-      // ---- probabilities: bf16 pairs back into the first 64 columns of this tile's S (the P V A operand)
-      float lsum = 0.0f;
+      if (q4 == 0 && lane == 0) F3_TRACE(t, j, 1);
+      if (TURNS) named_bar_sync(2 + t, 256);  // my turn on the MUFU
+      if (q4 == 0 && lane == 0) F3_TRACE(t, j, 3);
+      float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // this tile's row sum (relative to m_ref), 4 independent chains
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        uint32_t(&cur)[32] = v[c & 1];
+        if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, v[(c + 1) & 1]);
+        const float bh = (c < 2) ? bh0 : bh1;
+        float d = RELPOS ? bh - m_ref : -m_ref;  // +inf while m_ref = -inf: the first chunk always takes the exact path
+        float ymax[2] = {-INFINITY, -INFINITY};
+        float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         uint32_t pk[16];
-        if (RELPOS) {
-          const float d = ((c < 2) ? bh0 : bh1) - m_ref;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float e0 = ex2_approx(y[c * 32 + 2 * i] + d), e1 = ex2_approx(y[c * 32 + 2 * i + 1] + d);
-            lsum += e0 + e1;
-            pk[i] = pack_bf16(e0, e1);
+        for (int i = 0; i < 16; ++i) {
+          float y0, y1;
+          if (RELPOS) {
+            y0 = fmaf(__uint_as_float(cur[2 * i]), c1, tw[RELPOS ? (c & 1) * 32 + 2 * i : 0]);
+            y1 = fmaf(__uint_as_float(cur[2 * i + 1]), c1, tw[RELPOS ? (c & 1) * 32 + 2 * i + 1 : 0]);
+            ymax[0] = fmaxf(ymax[0], y0);
+            ymax[1] = fmaxf(ymax[1], y1);
+            y0 += d;
+            y1 += d;
+          } else {
+            ymax[0] = fmaxf(ymax[0], __uint_as_float(cur[2 * i]));  // raw scores: c1 > 0
+            ymax[1] = fmaxf(ymax[1], __uint_as_float(cur[2 * i + 1]));
+            y0 = fmaf(__uint_as_float(cur[2 * i]), c1, d);
+            y1 = fmaf(__uint_as_float(cur[2 * i + 1]), c1, d);
           }
-        } else {
-          const float d = -m_ref;
+          const float e0 = ex2_approx(y0), e1 = ex2_approx(y1);
+          cs[i & 3] += e0 + e1;
+          pk[i] = pack_bf16(e0, e1);
+        }
+        const float m_chunk = RELPOS ? fmaxf(ymax[0], ymax[1]) + bh : fmaxf(ymax[0], ymax[1]) * c1;
+        const bool need = m_chunk > m_ref + F3_TAU;
+        if (__any_sync(0xffffffffu, need)) {
+          // ---- exact path (rare after the first chunk of a row): raise the reference maximum.  s_full(j) implies that
+          // P(j-1) V has completed, so O is stable; the MMA thread does not touch this tile before p_full(j).
+          const float m_new = need ? m_chunk : m_ref;
+          const float alpha = ex2_approx(m_ref - m_new);  // 1 for lanes that did not need it, 0 on the very first chunk
+          if (j > 0) {
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) {
+              uint32_t o[16];
+              tmem_ld16(o_addr + k * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(o_addr + k * 16, o);
+            }
+          }
+          l_run *= alpha;
+          if (c > 0) {  // P chunks of this tile written against the old reference
+            tmem_st_wait();
+#pragma unroll
+            for (int k = 0; k < c; ++k) {
+              uint32_t o[16];
+              tmem_ld16(s_addr + k * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float lo = __uint_as_float(o[i] << 16) * alpha, hi2 = __uint_as_float(o[i] & 0xffff0000u) * alpha;
+                o[i] = pack_bf16(lo, hi2);
+              }
+              tmem_st16(s_addr + k * 16, o);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ls[i] *= alpha;
+          }
+          m_ref = m_new;
+          d = RELPOS ? bh - m_ref : -m_ref;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cs[i] = 0.0f;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float e0 = ex2_approx(fmaf(y[c * 32 + 2 * i], c1, d)), e1 = ex2_approx(fmaf(y[c * 32 + 2 * i + 1], c1, d));
-            lsum += e0 + e1;
+            float y0, y1;
+            if (RELPOS) {
+              y0 = fmaf(__uint_as_float(cur[2 * i]), c1, tw[RELPOS ? (c & 1) * 32 + 2 * i : 0]) + d;
+              y1 = fmaf(__uint_as_float(cur[2 * i + 1]), c1, tw[RELPOS ? (c & 1) * 32 + 2 * i + 1 : 0]) + d;
+            } else {
+              y0 = fmaf(__uint_as_float(cur[2 * i]), c1, d);
+              y1 = fmaf(__uint_as_float(cur[2 * i + 1]), c1, d);
+            }
+            const float e0 = ex2_approx(y0), e1 = ex2_approx(y1);
+            cs[i & 3] += e0 + e1;
             pk[i] = pack_bf16(e0, e1);
           }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ls[i] += cs[i];
         tmem_st16(s_addr + c * 16, pk);
+        if (c < 3) tmem_ld_wait();  // chunk c + 1 has landed
       }
-      l_run += lsum;
+      if (q4 == 0 && lane == 0) F3_TRACE(t, j, 4);
+      if (TURNS && (t == 0 || j + 1 < nk)) named_bar_arrive(3 - t, 256);  // hand the MUFU to the other tile
+      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       tmem_st_wait();
+      if (q4 == 0 && lane == 0) F3_TRACE(t, j, 5);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
@@ -393,19 +469,19 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   }
 }
 
-template <int HD, bool RELPOS>
+template <int HD, bool RELPOS, bool TURNS>
 static int launch_flash3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                          const FlashParams& p, cudaStream_t st) {
   using Cfg = Flash3Cfg<HD, RELPOS>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(flash3_kernel<HD, RELPOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+    if (cudaFuncSetAttribute(flash3_kernel<HD, RELPOS, TURNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
         cudaSuccess)
       return WM_ERR_CUDA;
     attr_set = true;
   }
   dim3 grid(p.Tq / 256, p.H, p.B);
-  flash3_kernel<HD, RELPOS><<<grid, F3_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, trel, p);
+  flash3_kernel<HD, RELPOS, TURNS><<<grid, F3_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, trel, p);
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
@@ -413,13 +489,24 @@ static int launch_flash3(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
 int flash3_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                     const FlashParams& p, int hd, cudaStream_t st) {
   if (p.Tq % 256 != 0 || p.Tk % 128 != 0 || p.Tk < 128) return WM_ERR_SHAPE;
+  const bool turns = p.turns != 0;
   if (p.use_relpos) {
     if (hd != 64 || p.Tq != 4096 || p.Tk != 4096) return WM_ERR_SHAPE;
-    return launch_flash3<64, true>(tq, tk, tv, trel, p, st);
+    return turns ? launch_flash3<64, true, true>(tq, tk, tv, trel, p, st) : launch_flash3<64, true, false>(tq, tk, tv, trel, p, st);
   }
-  if (hd == 64) return launch_flash3<64, false>(tq, tk, tv, trel, p, st);
-  if (hd == 128) return launch_flash3<128, false>(tq, tk, tv, trel, p, st);
+  if (hd == 64)
+    return turns ? launch_flash3<64, false, true>(tq, tk, tv, trel, p, st) : launch_flash3<64, false, false>(tq, tk, tv, trel, p, st);
+  if (hd == 128)
+    return turns ? launch_flash3<128, false, true>(tq, tk, tv, trel, p, st) : launch_flash3<128, false, false>(tq, tk, tv, trel, p, st);
   return WM_ERR_SHAPE;
 }
+
+#ifdef WM_F3_TRACE
+int flash3_read_trace(unsigned long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_f3_trace, sizeof(g_f3_trace)) == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+#else
+int flash3_read_trace(unsigned long long*) { return WM_ERR_ARCH; }
+#endif
 
 }  // namespace wm

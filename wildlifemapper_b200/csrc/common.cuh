@@ -30,6 +30,10 @@ namespace wm {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// Warp index as a value the compiler knows to be warp-uniform: role branches on it are uniform branches, so the
+// single-thread TMA / tcgen05 instructions inside them take their operands from uniform registers directly
+// (a branch on threadIdx-derived values makes ptxas wrap every UTCHMMA / UTMALDG in an ELECT / R2UR waterfall loop).
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -246,6 +250,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // ------------------------------------------------------------------ misc
+// Named barriers (ids 1..15; 0 is __syncthreads): `sync` waits until `count` threads have arrived, `arrive` only signals.
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

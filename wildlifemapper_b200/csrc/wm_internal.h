@@ -38,6 +38,7 @@ struct FlashParams {
   int q_col0, k_col0, v_col0;  // first column of head 0 inside the q / k / v tensor maps
   __nv_bfloat16* out;
   int ldo;
+  int turns;       // v3: the two softmax warpgroups take turns on the MUFU (A/B knob "flash_turns")
   int use_relpos;  // global 64x64 grid decomposed rel-pos; tables via tmap_rel ([256, HD]: rows 0..126 Rh, 128..254 Rw)
 };
 int flash_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
@@ -47,6 +48,8 @@ int flash2_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
                     const FlashParams& p, int hd, cudaStream_t st);
 int flash3_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                     const FlashParams& p, int hd, cudaStream_t st);
+
+int flash3_read_trace(unsigned long long* host_out);  // diagnostics build (-DWM_F3_TRACE) only
 
 struct WindowParams {
   int B, H;     // images, heads

@@ -22,6 +22,7 @@ SIGNATURES = {
     "wm_device_check": [],
     "wm_set_flash_version": [_i],
     "wm_set_option": [C.c_char_p, _i],
+    "wm_debug_flash_trace": [_p],
     "wm_gemm_bf16": [_p, _i64, _p, _i64, _p, _p, _i64, _i, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _p],
     "wm_conv3x3_nhwc_bf16": [_p, _p, _p, _p, _i, _i, _i, _p],
     "wm_layernorm": [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _f, _p],
@@ -61,7 +62,7 @@ def load() -> C.CDLL:
         fn.argtypes = argtypes
         fn.restype = C.c_char_p if name == "wm_last_error" else C.c_int
     _lib = lib
-    for env, opt in (("WM_FLASH_VERSION", b"flash_version"),):
+    for env, opt in (("WM_FLASH_VERSION", b"flash_version"), ("WM_FLASH_TURNS", b"flash_turns")):
         if os.environ.get(env):  # measurement knobs, see include/wm_b200.h
             lib.wm_set_option(opt, int(os.environ[env]))
     return lib

@@ -62,8 +62,8 @@ for name, m, n, k, has_bias, res_rows, o16, o32, act in SHAPES:
         out32 = res
     flop = 2.0 * m * n * k
     r = {"name": name, "M": m, "N": n, "K": k}
-    for bn in (256, 128):
-        if n < bn:
+    for bn in (512, 256):
+        if n < min(bn, 256) or (bn == 512 and n % 256):
             continue
         ms = timeit(lambda: ops.gemm(a, w, bias, res, res_rows, out16, out32, act, bn))
         r[f"wm_bn{bn}_ms"] = round(ms, 4)

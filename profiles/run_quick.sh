@@ -11,4 +11,4 @@ import json; d=json.load(open('gpurun_out/bench_${tag}.json')); print(d['value']
 if [ -z "$NO_SHAPES" ]; then timeout 600 python profiles/gemm_shapes.py 32 > gpurun_out/gemm_shapes_${tag}.jsonl 2> gpurun_out/gemm_shapes_${tag}.err; python -c "
 import json
 for l in open('gpurun_out/gemm_shapes_${tag}.jsonl'):
-    r=json.loads(l); print('%-18s wm256 %.4f ms %6.0f TF | cublas %.4f ms %6.0f TF | hbm %.4f' % (r['name'], r.get('wm_bn256_ms',0), r.get('wm_bn256_tflops',0), r['cublas_ms'], r['cublas_tflops'], r['min_hbm_ms']))"; fi
+    r=json.loads(l); print('%-18s pair %.4f ms %6.0f TF | 1cta %.4f ms %6.0f TF | cublas %.4f ms %6.0f TF | hbm %.4f' % (r['name'], r.get('wm_bn512_ms',0), r.get('wm_bn512_tflops',0), r.get('wm_bn256_ms',0), r.get('wm_bn256_tflops',0), r['cublas_ms'], r['cublas_tflops'], r['min_hbm_ms']))"; fi

@@ -32,6 +32,9 @@ def rel_err(got, ref):
     (128, 256, 64, 0), (256, 256, 128, 0), (1000, 768, 768, 0), (4096, 2304, 768, 0), (4096, 768, 3072, 0),
     (384, 128, 256, 0), (51, 8, 256, 0), (300, 4, 256, 0), (1632, 2048, 256, 0), (1632, 256, 2048, 0),
     (512, 1024, 1024, 128), (512, 1280, 1280, 0), (640, 192, 128, 64), (20000, 256, 768, 0),
+    # bn = 512: the CTA-pair kernel (256 x 256 tile per cluster of two CTAs), incl. ragged M and more tiles than clusters
+    (256, 256, 128, 512), (1000, 768, 768, 512), (4096, 2304, 768, 512), (300, 512, 64, 512), (20000, 256, 768, 512),
+    (40000, 1024, 256, 512), (32768, 768, 3072, 0),
 ])
 def test_gemm_matches_fp32(M, N, K, bn):
     a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
@@ -41,15 +44,16 @@ def test_gemm_matches_fp32(M, N, K, bn):
     assert rel_err(out, ref) < 2e-3  # bf16 products are exact in fp32; only accumulation order differs
 
 
+@pytest.mark.parametrize("bn", [0, 512])
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
-def test_gemm_epilogues(act):
+def test_gemm_epilogues(act, bn):
     M, N, K = 700, 768, 256
     a, w = rnd(M, K, seed=3), rnd(N, K, seed=4, scale=K ** -0.5)
     bias = rnd(N, seed=5, dtype=torch.float32)
     res = rnd(100, N, seed=6, dtype=torch.float32)
     o32 = torch.empty(M, N, device=DEV, dtype=torch.float32)
     o16 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
-    ops.gemm(a, w, bias, res, 100, o16, o32, act, 0)
+    ops.gemm(a, w, bias, res, 100, o16, o32, act, bn)
     y = a.float() @ w.float().t() + bias
     y = [y, torch.nn.functional.gelu(y), torch.relu(y), torch.sigmoid(y)][act]
     y = y + res[torch.arange(M, device=DEV) % 100]

@@ -92,7 +92,7 @@ int ensure_device() {
 
 // bf16 tensor map, SWIZZLE_128B, inner box = 64 elements (128 bytes).  dims/strides innermost first.
 int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-             const uint32_t* box, const char* what) {
+             const uint32_t* box, const char* what, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(WM_ERR_ALIGN, "%s: base pointer not 16-byte aligned", what);
   cuuint64_t gd[5];
   cuuint64_t gs[4];
@@ -106,7 +106,7 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, co
       gs[i - 1] = strides_bytes[i - 1];
     }
   }
-  CUresult r = g_dev.encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+  CUresult r = g_dev.encode(m, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(WM_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
@@ -123,6 +123,7 @@ int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, u
 
 int g_flash_version = 3;
 int g_flash_turns = 1;
+int g_gemm_pairs = 1;
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -138,6 +139,7 @@ int wm_set_option(const char* name, int value) {
   const std::string n(name ? name : "");
   if (n == "flash_version") return wm_set_flash_version(value);
   if (n == "flash_turns") { g_flash_turns = value != 0; return WM_OK; }
+  if (n == "gemm_pairs") { g_gemm_pairs = value != 0; return WM_OK; }
   return fail(WM_ERR_SHAPE, "wm_set_option: unknown option '%s'", n.c_str());
 }
 int wm_set_flash_version(int version) {
@@ -155,22 +157,45 @@ int wm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const f
   if (out_bf16 == nullptr && out_f32 == nullptr) return fail(WM_ERR_SHAPE, "wm_gemm_bf16: no output");
   if (act < 0 || act > 3) return fail(WM_ERR_SHAPE, "wm_gemm_bf16: bad act %d", act);
   if (residual != nullptr && res_mod <= 0) return fail(WM_ERR_SHAPE, "wm_gemm_bf16: res_mod must be > 0");
+  // tile selection: 512 = CTA-pair kernel (256 x 256 tile per pair of SMs) for the large GEMMs; 256 / 128 / 64 = single-CTA
+  // kernel with a 128 x bn tile
   int bn = bn_hint;
-  if (bn == 0) bn = (N >= 256) ? 256 : (N > 64 ? 128 : 64);
-  if (bn != 64 && bn != 128 && bn != 256) return fail(WM_ERR_SHAPE, "wm_gemm_bf16: bn_hint must be 0/64/128/256");
+  if (bn == 0) {
+    if (N % 256 == 0 && M >= 256 * (g_dev.num_sms / 2) && g_gemm_pairs) bn = 512;
+    else bn = (N >= 256) ? 256 : (N > 64 ? 128 : 64);
+  }
+  if (bn != 64 && bn != 128 && bn != 256 && bn != 512) return fail(WM_ERR_SHAPE, "wm_gemm_bf16: bn_hint must be 0/64/128/256/512");
+  if (bn == 512 && N % 256 != 0) return fail(WM_ERR_SHAPE, "wm_gemm_bf16: the CTA-pair kernel needs N %% 256 == 0");
   CUtensorMap ta, tw;
   if (int rc = make_map_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, "wm_gemm_bf16(A)")) return rc;
-  if (int rc = make_map_2d(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, "wm_gemm_bf16(W)")) return rc;
+  if (int rc = make_map_2d(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, bn == 512 ? 128u : (uint32_t)bn, "wm_gemm_bf16(W)")) return rc;
   wm::GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.residual = residual; p.ldr = (int)ldr; p.res_mod = res_mod > 0 ? res_mod : 1;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldc_bf16 = (int)ldc_bf16;
   p.out_f32 = out_f32; p.ldc_f32 = (int)ldc_f32;
   p.act = act; p.a_mode = 0; p.conv_C = 0;
-  p.vec_ok = (bias == nullptr || aligned16(bias)) && (residual == nullptr || (aligned16(residual) && ldr % 4 == 0)) &&
+  // 16-byte vector accesses to bias / residual / outputs at columns that are multiples of 4
+  p.vec_ok = (N % 4 == 0) && (bias == nullptr || aligned16(bias)) && (residual == nullptr || (aligned16(residual) && ldr % 4 == 0)) &&
              (out_bf16 == nullptr || (aligned16(out_bf16) && ldc_bf16 % 8 == 0)) &&
              (out_f32 == nullptr || (aligned16(out_f32) && ldc_f32 % 4 == 0));
-  return check_launch(wm::gemm_dispatch(ta, tw, p, bn, g_dev.num_sms, (cudaStream_t)stream), "wm_gemm_bf16");
+  // TMA-store epilogue: exactly one output, 16-byte aligned rows; bf16 stores are 64 columns wide (tiles of >= 128 columns)
+  p.res_inplace = residual != nullptr && residual == out_f32 && ldr == ldc_f32 && res_mod >= M;
+  p.tma_out = p.vec_ok && N % 8 == 0 && ((out_bf16 != nullptr) != (out_f32 != nullptr)) && (out_f32 != nullptr || bn >= 128) && N >= 64;
+  CUtensorMap tc16 = ta, tc32 = ta;
+  if (p.tma_out) {
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    if (out_bf16 != nullptr) {
+      const uint64_t strides[1] = {(uint64_t)ldc_bf16 * 2};
+      const uint32_t box[2] = {64, 32};
+      if (int rc = make_map(&tc16, out_bf16, 2, dims, strides, box, "wm_gemm_bf16(out_bf16)")) return rc;
+    } else {
+      const uint64_t strides[1] = {(uint64_t)ldc_f32 * 4};
+      const uint32_t box[2] = {32, 32};
+      if (int rc = make_map(&tc32, out_f32, 2, dims, strides, box, "wm_gemm_bf16(out_f32)", CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return rc;
+    }
+  }
+  return check_launch(wm::gemm_dispatch(ta, tw, tc16, tc32, p, bn, g_dev.num_sms, (cudaStream_t)stream), "wm_gemm_bf16");
 }
 
 int wm_conv3x3_nhwc_bf16(const void* X, const void* W, void* out_bf16, float* out_f32, int B, int C, int N,
@@ -191,8 +216,9 @@ int wm_conv3x3_nhwc_bf16(const void* X, const void* W, void* out_bf16, float* ou
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldc_bf16 = N;
   p.out_f32 = out_f32; p.ldc_f32 = N;
   p.a_mode = 1; p.conv_C = C;
-  p.vec_ok = (out_bf16 == nullptr || aligned16(out_bf16)) && (out_f32 == nullptr || aligned16(out_f32));
-  return check_launch(wm::gemm_dispatch(ta, tw, p, bn, g_dev.num_sms, (cudaStream_t)stream), "wm_conv3x3_nhwc_bf16");
+  p.vec_ok = (N % 4 == 0) && (out_bf16 == nullptr || aligned16(out_bf16)) && (out_f32 == nullptr || aligned16(out_f32));
+  p.tma_out = 0; p.res_inplace = 0;
+  return check_launch(wm::gemm_dispatch(ta, tw, ta, ta, p, bn, g_dev.num_sms, (cudaStream_t)stream), "wm_conv3x3_nhwc_bf16");
 }
 
 int wm_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, const float* add,

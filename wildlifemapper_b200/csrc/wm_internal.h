@@ -22,14 +22,17 @@ struct GemmParams {
   int ldc_bf16;
   float* out_f32;  // nullable
   int ldc_f32;
-  int act;     // 0 none, 1 erf-GELU, 2 ReLU
-  int vec_ok;  // 16-byte vector epilogue allowed (alignment verified on host)
+  int act;     // 0 none, 1 erf-GELU, 2 ReLU, 3 sigmoid
+  int vec_ok;  // 16-byte vector accesses to bias / residual allowed (alignment verified on host)
+  int tma_out; // outputs are written with TMA stores from swizzled smem staging (tensor maps tc16 / tc32)
+  int res_inplace;  // residual == out_f32 (same rows, same leading dim): fp32 output is a TMA reduce-add
   int a_mode;  // 0: A is [M,K] row-major; 1: implicit 3x3 conv over NHWC [B,64,64,conv_C]
   int conv_C;
 };
 
-int gemm_dispatch(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, int bn, int num_sms,
-                  cudaStream_t st);
+// tc16 / tc32: output tensor maps (bf16 box 64 x 32, fp32 box 32 x 32, SWIZZLE_128B); only read when p.tma_out
+int gemm_dispatch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc16, const CUtensorMap& tc32,
+                  const GemmParams& p, int bn, int num_sms, cudaStream_t st);
 
 struct FlashParams {
   // O[b, t, h*HD + d] = softmax_k( scale * q.k + bias ) v   over Tk keys, per (image b, head h)

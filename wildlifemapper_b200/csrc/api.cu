@@ -181,7 +181,8 @@ int wm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const f
              (out_f32 == nullptr || (aligned16(out_f32) && ldc_f32 % 4 == 0));
   // TMA-store epilogue: exactly one output, 16-byte aligned rows; bf16 stores are 64 columns wide (tiles of >= 128 columns)
   p.res_inplace = residual != nullptr && residual == out_f32 && ldr == ldc_f32 && res_mod >= M;
-  p.tma_out = p.vec_ok && N % 8 == 0 && ((out_bf16 != nullptr) != (out_f32 != nullptr)) && (out_f32 != nullptr || bn >= 128) && N >= 64;
+  const bool dual = out_bf16 != nullptr && out_f32 != nullptr;
+  p.tma_out = (p.vec_ok && N % 8 == 0 && N >= 64 && (out_f32 != nullptr || bn >= 128) && (!dual || bn == 512)) ? (dual ? 2 : 1) : 0;
   CUtensorMap tc16 = ta, tc32 = ta;
   if (p.tma_out) {
     const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
@@ -189,7 +190,8 @@ int wm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const f
       const uint64_t strides[1] = {(uint64_t)ldc_bf16 * 2};
       const uint32_t box[2] = {64, 32};
       if (int rc = make_map(&tc16, out_bf16, 2, dims, strides, box, "wm_gemm_bf16(out_bf16)")) return rc;
-    } else {
+    }
+    if (out_f32 != nullptr) {
       const uint64_t strides[1] = {(uint64_t)ldc_f32 * 4};
       const uint32_t box[2] = {32, 32};
       if (int rc = make_map(&tc32, out_f32, 2, dims, strides, box, "wm_gemm_bf16(out_f32)", CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return rc;

@@ -69,6 +69,40 @@ __device__ __forceinline__ float gelu_erf(float x) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// Two GELUs at once on the packed fp32x2 FMA path of sm_100 (FFMA2 / FMUL2: one issue slot per pair)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const float z0 = fminf(fmaxf(x0 * 0.70710678118654752f, -3.0f), 3.0f);
+  const float z1 = fminf(fmaxf(x1 * 0.70710678118654752f, -3.0f), 3.0f);
+  const uint64_t z = pk2(z0, z1);
+  const uint64_t z2 = mul2(z, z);
+  uint64_t pl = fma2(pk2(4.074191295444507e-08f, 4.074191295444507e-08f), z2, pk2(-1.944815949173062e-06f, -1.944815949173062e-06f));
+  pl = fma2(pl, z2, pk2(4.106042979401536e-05f, 4.106042979401536e-05f));
+  pl = fma2(pl, z2, pk2(-0.0005110361380502582f, -0.0005110361380502582f));
+  pl = fma2(pl, z2, pk2(0.004235424567013979f, 0.004235424567013979f));
+  pl = fma2(pl, z2, pk2(-0.025102855637669563f, -0.025102855637669563f));
+  pl = fma2(pl, z2, pk2(0.11107932776212692f, 0.11107932776212692f));
+  pl = fma2(pl, z2, pk2(-0.375314861536026f, -0.375314861536026f));
+  pl = fma2(pl, z2, pk2(1.1282684803009033f, 1.1282684803009033f));
+  const uint64_t hx = mul2(pk2(x0, x1), pk2(0.5f, 0.5f));
+  const uint64_t r = fma2(hx, mul2(pl, z), hx);
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(r));
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == 1) return gelu_erf(x);
   if (act == 2) return fmaxf(x, 0.0f);
@@ -145,7 +179,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
               if (n0 + j < p.N) f[j] += __ldg(p.bias + n0 + j);
           }
         }
-        if (p.act != 0) {
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) gelu_erf2(f[2 * j], f[2 * j + 1]);
+        } else if (p.act != 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
         }
@@ -164,7 +201,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         }
         if (p.out_f32 != nullptr) {
           // ---- fp32 output: 32 columns = one 128-byte swizzled row per lane
-          if (lane == 0) tma_store_wait_read();  // the previous store of this warp has finished reading the staging buffer
+          if (lane == 0) tma_store_wait_read();  // the previous stores of this warp have finished reading the staging buffers
           __syncwarp();
 #pragma unroll
           for (int k = 0; k < 8; ++k)
@@ -177,23 +214,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
             else tma_store_2d(tc32, stage, n0, row0);
             tma_store_commit();
           }
-        } else {
+        }
+        if (p.out_bf16 != nullptr) {
           // ---- bf16 output: two chunks share one 128-byte row (64 columns): even chunk -> 16-byte pieces 0..3, odd -> 4..7.
           // An unpaired last chunk only happens at the right edge of the matrix, where TMA clips the unwritten half.
-          if ((c & 1) == 0) {
+          // With both outputs (tma_out == 2, CTA-pair kernel) the bf16 rows use the warp's second staging buffer; the
+          // wait above (every chunk) already covers its reuse.
+          const uint32_t off16 = (p.out_f32 != nullptr) ? 4096u : 0u;
+          if ((c & 1) == 0 && p.out_f32 == nullptr) {
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            sts128(st_row + (((uint32_t)((c & 1) * 4 + k) ^ sw) << 4), pack_bf16(f[8 * k], f[8 * k + 1]),
+            sts128(st_row + off16 + (((uint32_t)((c & 1) * 4 + k) ^ sw) << 4), pack_bf16(f[8 * k], f[8 * k + 1]),
                    pack_bf16(f[8 * k + 2], f[8 * k + 3]), pack_bf16(f[8 * k + 4], f[8 * k + 5]),
                    pack_bf16(f[8 * k + 6], f[8 * k + 7]));
           if ((c & 1) == 1 || c == nact - 1) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(tc16, stage, n0 - (c & 1) * 32, row0);
+              tma_store_2d(tc16, stage + off16, n0 - (c & 1) * 32, row0);
               tma_store_commit();
             }
           }
@@ -399,14 +440,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 //   empty / tfull   are signalled in BOTH CTAs by multicast tcgen05.commit
 //   tempty          lives in the leader: 2 x 8 epilogue warps arrive (the peer's remotely)
 struct Gemm2Cfg {
-  static constexpr int kStages = 6;
+  static constexpr int kStages = 5;
   static constexpr int A_BYTES = 128 * BK * 2;   // this CTA's 128 rows of A
   static constexpr int B_BYTES = 128 * BK * 2;   // this CTA's half of the 256 W rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OFF_EPI = kStages * STAGE_BYTES;
-  static constexpr int EPI_BYTES = kEpiWarps * 4096;
+  static constexpr int EPI_BYTES = kEpiWarps * 8192;  // two 4 KB staging buffers per epilogue warp (dual fp32 + bf16 output)
   static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static constexpr int TMEM_COLS = 512;  // 2 accumulator stages x 256 columns
 };
 
@@ -512,7 +554,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else {
     WM_SETMAXNREG_INC();
     // ------------------------------------------------------------ epilogue (both CTAs: own 128 rows of the tile)
-    uint8_t* stage_buf = smem + Cfg::OFF_EPI + (warp - 4) * 4096;
+    uint8_t* stage_buf = smem + Cfg::OFF_EPI + (warp - 4) * 8192;
     int as = 0;
     uint32_t aphase = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {

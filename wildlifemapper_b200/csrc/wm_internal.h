@@ -24,7 +24,7 @@ struct GemmParams {
   int ldc_f32;
   int act;     // 0 none, 1 erf-GELU, 2 ReLU, 3 sigmoid
   int vec_ok;  // 16-byte vector accesses to bias / residual allowed (alignment verified on host)
-  int tma_out; // outputs are written with TMA stores from swizzled smem staging (tensor maps tc16 / tc32)
+  int tma_out; // 1: the single output is written with TMA stores from swizzled smem staging (tc16 / tc32); 2: both outputs (CTA-pair kernel)
   int res_inplace;  // residual == out_f32 (same rows, same leading dim): fp32 output is a TMA reduce-add
   int a_mode;  // 0: A is [M,K] row-major; 1: implicit 3x3 conv over NHWC [B,64,64,conv_C]
   int conv_C;

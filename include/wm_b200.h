@@ -44,7 +44,7 @@ int wm_device_check(void);
  * kernel; also the path taken when Tq % 256 != 0).  Kept selectable for A/B measurements. */
 int wm_set_flash_version(int version);
 /* Tuning knobs (for A/B measurements): "flash_version" (1|2|3), "flash_turns" (0|1: v3 softmax warpgroups take turns
- * on the MUFU), "gemm_pairs" (0|1: large GEMMs on the CTA-pair kernel). */
+ * on the MUFU), "gemm_pairs" (0|1: large GEMMs on the CTA-pair kernel), "window_version" (1|2: windowed-attention kernel generation). */
 int wm_set_option(const char* name, int value);
 /* Diagnostics build only (csrc/build.sh with -DWM_F3_TRACE): copy the SM-clock event trace of CTA (0,0,0) of the last
  * v3 flash-attention launch to host_out[3][64][4]; returns WM_ERR_ARCH in the product build. */

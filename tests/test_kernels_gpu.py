@@ -237,8 +237,17 @@ def test_attn_flash_global_relpos(flash_version):
     assert (out.float() - ref).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize("B,H", [(1, 2), (2, 12)])
-def test_attn_window(B, H):
+@pytest.fixture(params=[2, 1])
+def window_version(request):
+    """Both windowed-attention kernel generations stay parity-checked (2 = default)."""
+    from wildlifemapper_b200 import lib
+    lib.call("wm_set_option", b"window_version", request.param)
+    yield request.param
+    lib.call("wm_set_option", b"window_version", 2)
+
+
+@pytest.mark.parametrize("B,H", [(1, 2), (2, 12), (3, 5)])
+def test_attn_window(B, H, window_version):
     hd, S = 64, 14
     D = H * hd
     qkv = rnd(B, 64, 64, 3 * D, seed=29)

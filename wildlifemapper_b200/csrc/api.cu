@@ -124,6 +124,7 @@ int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, u
 int g_flash_version = 3;
 int g_flash_turns = 1;
 int g_gemm_pairs = 1;
+int g_window_version = 2;
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -140,6 +141,7 @@ int wm_set_option(const char* name, int value) {
   if (n == "flash_version") return wm_set_flash_version(value);
   if (n == "flash_turns") { g_flash_turns = value != 0; return WM_OK; }
   if (n == "gemm_pairs") { g_gemm_pairs = value != 0; return WM_OK; }
+  if (n == "window_version") { g_window_version = value == 1 ? 1 : 2; return WM_OK; }
   return fail(WM_ERR_SHAPE, "wm_set_option: unknown option '%s'", n.c_str());
 }
 int wm_set_flash_version(int version) {
@@ -312,18 +314,34 @@ int wm_attn_window(const void* qkv, const void* rel_table, void* out_bf16, int B
   if (int rc = ensure_device()) return rc;
   if (B <= 0 || B > 65535 || H <= 0 || D != H * 64) return fail(WM_ERR_SHAPE, "wm_attn_window: needs D == H*64 (hd = 64)");
   if (!aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_attn_window: alignment");
-  CUtensorMap tq, tkv, trel;
+  CUtensorMap tq, tkv, trel, tout;
   const uint64_t W3 = (uint64_t)3 * D;
   const uint64_t dims[4] = {W3, 64, 64, (uint64_t)B};
   const uint64_t strides[3] = {W3 * 2, W3 * 2 * 64, W3 * 2 * 4096};
+  wm::WindowParams p{};
+  p.B = B; p.H = H; p.scale = scale; p.D = D;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (g_window_version == 2) {
+    // dense 14-wide boxes: a query half is 7 window rows x 14, K / V are the whole 14 x 14 window; zero padding of the
+    // 70x70 grid = TMA out-of-bounds fill on loads, the crop back to 64x64 = TMA bounds check on the output store
+    const uint32_t box_q[4] = {64, 14, 7, 1};
+    const uint32_t box_kv[4] = {64, 14, 14, 1};
+    const uint64_t odims[4] = {(uint64_t)D, 64, 64, (uint64_t)B};
+    const uint64_t ostrides[3] = {(uint64_t)D * 2, (uint64_t)D * 2 * 64, (uint64_t)D * 2 * 4096};
+    const uint64_t rdims[2] = {64, 64};
+    const uint64_t rstrides[1] = {128};
+    const uint32_t rbox[2] = {64, 27};
+    if (int rc = make_map(&tq, qkv, 4, dims, strides, box_q, "wm_attn_window(q)")) return rc;
+    if (int rc = make_map(&tkv, qkv, 4, dims, strides, box_kv, "wm_attn_window(kv)")) return rc;
+    if (int rc = make_map(&trel, rel_table, 2, rdims, rstrides, rbox, "wm_attn_window(rel)")) return rc;
+    if (int rc = make_map(&tout, out_bf16, 4, odims, ostrides, box_q, "wm_attn_window(out)")) return rc;
+    return check_launch(wm::window2_dispatch(tq, tkv, trel, tout, p, g_dev.num_sms, (cudaStream_t)stream), "wm_attn_window(v2)");
+  }
   const uint32_t box_q[4] = {64, 16, 7, 1};
   const uint32_t box_kv[4] = {64, 16, 14, 1};
   if (int rc = make_map(&tq, qkv, 4, dims, strides, box_q, "wm_attn_window(q)")) return rc;
   if (int rc = make_map(&tkv, qkv, 4, dims, strides, box_kv, "wm_attn_window(kv)")) return rc;
   if (int rc = make_map_2d(&trel, rel_table, 64, 64, 64, 64, "wm_attn_window(rel)")) return rc;
-  wm::WindowParams p{};
-  p.B = B; p.H = H; p.scale = scale; p.D = D;
-  p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   return check_launch(wm::window_dispatch(tq, tkv, trel, p, (cudaStream_t)stream), "wm_attn_window");
 }
 

@@ -1,0 +1,373 @@
+// Fused 14x14 windowed attention with decomposed rel-pos bias, second generation (sm_100a, tcgen05 / TMEM / TMA).
+// Same math and reference sites as attn_window.cu (image_encoder.py:188-204, 246-311, 347-383; pad keys: SURVEY.md
+// section 0.2).  The first kernel ran one non-pipelined CTA per (half window, head): TMA -> MMA -> softmax -> MMA ->
+// store strictly in sequence, ~7.4 us per CTA and 88 TFLOP/s (profiles/r01a_ncu_window_summary.txt).  This one is
+// PERSISTENT and pipelined:
+//
+//   * work item = one (image, window, head): K and V are loaded once for both 98-query halves (7 window rows x 14,
+//     dense 14-wide TMA boxes: no 16-wide padding columns, no masked keys);
+//   * S' = Q [K ; Rh ; Rw]^T is ONE 128 x 256 x 64 MMA group: the 196 score columns and the 27 + 27 rel-pos table
+//     products T_h = q.Rh, T_w = q.Rw come out of the same instruction (the table rows sit behind the key rows of the
+//     K stage buffers, loaded once per CTA);
+//   * the probabilities never touch shared memory: bf16 pairs are written back over the consumed score columns in
+//     tensor memory and the P V MMA reads its A operand from TMEM; O lands in the (by then dead) table columns;
+//   * the two query halves ping-pong: the MMA warp serves tile 0 (P V, next item's S') while the softmax warps of
+//     tile 1 run their exp2 pass, and vice versa; K/V stages are double buffered, Q tiles are reloaded as soon as
+//     their S' has been issued;
+//   * the output leaves as a 4-D TMA store (box 64 ch x 14 x 7): the crop of the padded 70x70 grid back to 64x64 is
+//     the TMA bounds check.
+//
+//   warp 0       TMA producer          warp 1  tcgen05.mma issuer          warp 2  TMEM allocator
+//   warps 4-7    softmax / output of query tile 0     warps 8-11  of query tile 1     (thread = one query row)
+#include "common.cuh"
+#include "wm_internal.h"
+
+namespace wm {
+
+constexpr int W2_THREADS = 384;
+constexpr float W2_LOG2E = 1.4426950408889634f;
+constexpr float W2_TAU = 8.0f;
+constexpr int W2_Q_BYTES = 16384;                 // 128 rows x 128 B (98 loaded)
+constexpr int W2_K_BYTES = 32768;                 // 256 rows: 196 keys, 27 Rh, 27 Rw, 6 zero
+constexpr int W2_V_BYTES = 208 * 128;             // 196 keys + 12 zero rows (K dimension of P V = 13 x 16)
+constexpr int W2_T_LD = 55;                       // fp32 row stride of the per-thread bias scratch (odd: conflict-free)
+constexpr int W2_SCR_BYTES = 128 * W2_T_LD * 4;   // 28160 B, also the output staging (98 x 128 B)
+constexpr int W2_OFF_Q = 0;                                  // [2 tiles]
+constexpr int W2_OFF_K = W2_OFF_Q + 2 * W2_Q_BYTES;          // [2 stages]
+constexpr int W2_OFF_V = W2_OFF_K + 2 * W2_K_BYTES;          // [2 stages]
+constexpr int W2_OFF_SCR = W2_OFF_V + 2 * W2_V_BYTES + 1024; // [2 tiles], 1024-aligned (W2_V_BYTES is a multiple of 1024)
+constexpr int W2_SCR_STRIDE = 28672;
+constexpr int W2_OFF_BAR = W2_OFF_SCR + 2 * W2_SCR_STRIDE;
+constexpr int W2_SMEM_BYTES = W2_OFF_BAR + 256 + 1024;
+static_assert(W2_SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(W2_OFF_SCR % 1024 == 0 && W2_SCR_STRIDE % 1024 == 0, "staging alignment");
+constexpr int W2_COL_T = 196;   // T_h at S' columns 196..222, T_w at 223..249
+constexpr int W2_COL_O = 192;   // O_t (64 columns) over the consumed score / table columns
+
+__global__ void __launch_bounds__(W2_THREADS, 1)
+window2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+               const __grid_constant__ CUtensorMap tmap_rel, const __grid_constant__ CUtensorMap tmap_out,
+               const WindowParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W2_OFF_BAR);
+  uint64_t* k_full = bars + 0;    // [2 stages]
+  uint64_t* k_empty = bars + 2;
+  uint64_t* v_full = bars + 4;
+  uint64_t* v_empty = bars + 6;
+  uint64_t* q_full = bars + 8;    // [2 tiles]
+  uint64_t* q_empty = bars + 10;
+  uint64_t* s_full = bars + 12;   // S'_t complete
+  uint64_t* p_full = bars + 14;   // P_t stored (4 warps)
+  uint64_t* o_full = bars + 16;   // O_t complete
+  uint64_t* s_free = bars + 18;   // O_t read back: the TMEM columns of tile t may be overwritten (4 warps)
+  uint64_t* tab_full = bars + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  const int items_total = p.B * 25 * p.H;
+  const int n_items = (items_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // this CTA: blockIdx.x + n * gridDim.x
+
+  // zero rows that no TMA box ever writes: keys 196..207 of both V stages, rows 250..255 of both K stages
+  for (int i = threadIdx.x; i < 2 * (1536 / 16); i += W2_THREADS)
+    reinterpret_cast<uint4*>(smem + W2_OFF_V + (i / 96) * W2_V_BYTES + 196 * 128)[i % 96] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 2 * (768 / 16); i += W2_THREADS)
+    reinterpret_cast<uint4*>(smem + W2_OFF_K + (i / 48) * W2_K_BYTES + 250 * 128)[i % 48] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+    tma_prefetch_desc(&tmap_out);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 4);
+    }
+    mbar_init(tab_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int n, int& b, int& wy, int& wx, int& h) {  // item n of this CTA
+    const int it = (int)blockIdx.x + n * (int)gridDim.x;
+    h = it % p.H;
+    const int bw = it / p.H;
+    const int win = bw % 25;
+    b = bw / 25;
+    wy = win / 5;
+    wx = win % 5;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {  // rel-pos tables behind the key rows of both K stages (table tensor [64,64]: rows 0..26 Rh, 32..58 Rw)
+      mbar_arrive_expect_tx(tab_full, 4 * 27 * 128);
+      for (int s = 0; s < 2; ++s) {
+        tma_load_2d(smem + W2_OFF_K + s * W2_K_BYTES + 196 * 128, &tmap_rel, tab_full, 0, 0);
+        tma_load_2d(smem + W2_OFF_K + s * W2_K_BYTES + 223 * 128, &tmap_rel, tab_full, 0, 32);
+      }
+    }
+    __syncwarp();
+    for (int n = 0; n < n_items; ++n) {
+      int b, wy, wx, h;
+      decode(n, b, wy, wx, h);
+      const int st = n & 1;
+      const uint32_t ph = (uint32_t)(n >> 1) & 1u;
+      mbar_wait(&k_empty[st], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&k_full[st], 196 * 128);
+        tma_load_4d(smem + W2_OFF_K + st * W2_K_BYTES, &tmap_kv, &k_full[st], p.D + h * 64, wx * 14, wy * 14, b);
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&q_empty[t], (uint32_t)(n & 1) ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[t], 98 * 128);
+          tma_load_4d(smem + W2_OFF_Q + t * W2_Q_BYTES, &tmap_q, &q_full[t], h * 64, wx * 14, wy * 14 + t * 7, b);
+        }
+        __syncwarp();
+      }
+      mbar_wait(&v_empty[st], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&v_full[st], 196 * 128);
+        tma_load_4d(smem + W2_OFF_V + st * W2_V_BYTES, &tmap_kv, &v_full[st], 2 * p.D + h * 64, wx * 14, wy * 14, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    // per iteration n:  P_0 V (item n-1), S'_0 (item n), P_1 V (item n-1), S'_1 (item n)  -- each tile's next S' is
+    // issued right behind its P V, so the two tiles drift half a period apart and hide each other's round trips
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 256, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // A = P from TMEM, V MN-major
+    const bool leader = elect_one();
+    mbar_wait(tab_full, 0);
+    for (int n = 0; n <= n_items; ++n) {
+      const int st = n & 1;
+      const uint32_t ph = (uint32_t)(n >> 1) & 1u;
+      const int pst = (n - 1) & 1;
+      const uint32_t pph = (uint32_t)((n - 1) >> 1) & 1u;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t s_col = tmem_base + t * 256;
+        if (n > 0) {
+          mbar_wait(&p_full[t], (uint32_t)(n - 1) & 1u);
+          if (t == 0) mbar_wait(&v_full[pst], pph);
+          tc_fence_after();
+          if (leader) {
+            const uint64_t vd = make_sdesc_sw128(smem_u32(smem + W2_OFF_V + pst * W2_V_BYTES), 16, 1024);
+#pragma unroll
+            for (int ks = 0; ks < 13; ++ks)  // 208 keys, 16 per MMA; P_t: 8 TMEM columns per step; V: 2048 B per step
+              umma_bf16_ts(s_col + W2_COL_O, s_col + ks * 8, vd + (uint32_t)(ks * (2048 >> 4)), idesc_pv, ks != 0);
+            umma_commit(&o_full[t]);
+            if (t == 1) umma_commit(&v_empty[pst]);
+          }
+          __syncwarp();
+        }
+        if (n < n_items) {
+          if (n > 0) mbar_wait(&s_free[t], (uint32_t)(n - 1) & 1u);
+          mbar_wait(&q_full[t], (uint32_t)n & 1u);
+          if (t == 0) mbar_wait(&k_full[st], ph);
+          tc_fence_after();
+          if (leader) {
+            const uint64_t qd = make_sdesc_sw128(smem_u32(smem + W2_OFF_Q + t * W2_Q_BYTES), 16, 1024);
+            const uint64_t kd = make_sdesc_sw128(smem_u32(smem + W2_OFF_K + st * W2_K_BYTES), 16, 1024);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_bf16(s_col, qd + 2 * ks, kd + 2 * ks, idesc_s, ks != 0);
+            umma_commit(&s_full[t]);
+            umma_commit(&q_empty[t]);
+            if (t == 1) umma_commit(&k_empty[st]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ softmax / output of query tile t
+    const int t = (warp - 4) >> 2;
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;                 // query row of the tile == TMEM lane (rows >= 98 are unused)
+    const int yy = r / 14, x = r - yy * 14;
+    const int y = t * 7 + yy;                     // row inside the 14x14 window
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + t * 256;
+    const float c1 = p.scale * W2_LOG2E;
+    uint8_t* scr = smem + W2_OFF_SCR + t * W2_SCR_STRIDE;
+    float* sT = reinterpret_cast<float*>(scr) + r * W2_T_LD;
+    const uint32_t st_row = smem_u32(scr) + (uint32_t)r * 128u;
+    const int bar_id = 4 + t;                     // named barrier of this warpgroup
+
+    for (int n = 0; n < n_items; ++n) {
+      int b, wy, wx, h;
+      decode(n, b, wy, wx, h);
+      mbar_wait(&s_full[t], (uint32_t)n & 1u);
+      tc_fence_after();
+      // ---- rel-pos bias of this row: T_h[y - kh + 13], T_w[x - kw + 13] (columns 196..249), via the per-thread scratch
+      uint32_t v[2][32];
+      tmem_ld32(lane_addr + 192, v[0]);
+      tmem_ld32(lane_addr + 224, v[1]);
+      if (n > 0) {  // the previous item's output store must have finished reading the staging area (= this scratch)
+        if (warp == 4 + 4 * t && lane == 0) tma_store_wait_read();
+        named_bar_sync(bar_id, 128);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 4; i < 32; ++i) sT[i - 4] = __uint_as_float(v[0][i]) * W2_LOG2E;
+#pragma unroll
+      for (int i = 0; i < 26; ++i) sT[28 + i] = __uint_as_float(v[1][i]) * W2_LOG2E;
+      __syncwarp();
+      float bh[14], bw[14];
+#pragma unroll
+      for (int k = 0; k < 14; ++k) {
+        bh[k] = sT[y - k + 13];
+        bw[k] = sT[27 + x - k + 13];
+      }
+      // ---- one pass over the 196 scores in 32-column chunks (optimistic exp2 against the running reference maximum,
+      // exact redo from registers when a chunk exceeds it by more than 2^TAU; see attn_flash3.cu).  P chunk c (16
+      // columns of bf16 pairs) overwrites score columns [16c, 16c+16), which chunk c/2 has already consumed.
+      tmem_ld32(lane_addr, v[0]);
+      tmem_ld_wait();
+      float m_ref = -INFINITY;
+      float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int c = 0; c < 7; ++c) {
+        uint32_t(&cur)[32] = v[c & 1];
+        if (c < 6) tmem_ld32(lane_addr + (c + 1) * 32, v[(c + 1) & 1]);
+        constexpr int NV_FULL = 32;
+        const int nv = (c < 6) ? NV_FULL : 4;  // valid scores in this chunk (keys 192..195 in the last one)
+        float e[32];
+        float ymax[2] = {-INFINITY, -INFINITY};
+        float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < nv) {
+            const int k = c * 32 + i;          // key index (compile time): window row k / 14, column k % 14
+            const float yv = fmaf(__uint_as_float(cur[i]), c1, bh[k / 14] + bw[k % 14]);
+            ymax[i & 1] = fmaxf(ymax[i & 1], yv);
+            e[i] = ex2_approx(yv - m_ref);
+            cs[i & 3] += e[i];
+          } else {
+            e[i] = 0.0f;                       // pad keys 196..207
+          }
+        }
+        const float m_chunk = fmaxf(ymax[0], ymax[1]);
+        const bool need = m_chunk > m_ref + W2_TAU;  // always true for the first chunk
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? m_chunk : m_ref;
+          const float alpha = ex2_approx(m_ref - m_new);
+          if (c > 0) {  // P chunks of this row written against the old reference
+            tmem_st_wait();
+#pragma unroll
+            for (int kk = 0; kk < c; ++kk) {
+              uint32_t o[16];
+              tmem_ld16(lane_addr + kk * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float lo = __uint_as_float(o[i] << 16) * alpha, hi2 = __uint_as_float(o[i] & 0xffff0000u) * alpha;
+                o[i] = pack_bf16(lo, hi2);
+              }
+              tmem_st16(lane_addr + kk * 16, o);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ls[i] *= alpha;
+          }
+          m_ref = m_new;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cs[i] = 0.0f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < nv) {
+              const int k = c * 32 + i;
+              const float yv = fmaf(__uint_as_float(cur[i]), c1, bh[k / 14] + bw[k % 14]);
+              e[i] = ex2_approx(yv - m_ref);
+              cs[i & 3] += e[i];
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ls[i] += cs[i];
+        if (c < 6) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(e[2 * i], e[2 * i + 1]);
+          tmem_st16(lane_addr + c * 16, pk);
+          tmem_ld_wait();  // chunk c + 1 has landed
+        } else {
+          uint32_t pk[8];  // keys 192..207
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(e[2 * i], e[2 * i + 1]);
+          tmem_st8(lane_addr + 96, pk);
+        }
+      }
+      const float l_row = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+
+      // ---- output: O_t / l -> bf16 -> swizzled staging -> 4-D TMA store (the crop to the 64x64 image is the bounds check)
+      mbar_wait(&o_full[t], (uint32_t)n & 1u);
+      tc_fence_after();
+      tmem_ld32(lane_addr + W2_COL_O, v[0]);
+      tmem_ld32(lane_addr + W2_COL_O + 32, v[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);  // the MMA warp may overwrite this tile's TMEM columns
+      const float inv_l = 1.0f / l_row;
+      if (r < 98) {
+#pragma unroll
+        for (int hv = 0; hv < 2; ++hv)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t(&o)[32] = v[hv];
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + (((uint32_t)(hv * 4 + k) ^ (uint32_t)(r & 7)) << 4)),
+                         "r"(pack_bf16(__uint_as_float(o[8 * k]) * inv_l, __uint_as_float(o[8 * k + 1]) * inv_l)),
+                         "r"(pack_bf16(__uint_as_float(o[8 * k + 2]) * inv_l, __uint_as_float(o[8 * k + 3]) * inv_l)),
+                         "r"(pack_bf16(__uint_as_float(o[8 * k + 4]) * inv_l, __uint_as_float(o[8 * k + 5]) * inv_l)),
+                         "r"(pack_bf16(__uint_as_float(o[8 * k + 6]) * inv_l, __uint_as_float(o[8 * k + 7]) * inv_l))
+                         : "memory");
+          }
+      }
+      fence_proxy_async();
+      named_bar_sync(bar_id, 128);
+      if (warp == 4 + 4 * t && lane == 0) {
+        tma_store_4d(&tmap_out, scr, h * 64, wx * 14, wy * 14 + t * 7, b);
+        tma_store_commit();
+      }
+    }
+    if (warp == 4 + 4 * t && lane == 0) tma_store_wait_read();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// tq: box (64, 14, 7, 1) over qkv [B,64,64,3D]; tkv: box (64, 14, 14, 1); trel: box (64, 27) over the [64,64] table;
+// tout: box (64, 14, 7, 1) over out [B,64,64,D]
+int window2_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const CUtensorMap& tout,
+                     const WindowParams& p, int num_sms, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(window2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM_BYTES) != cudaSuccess)
+      return WM_ERR_CUDA;
+    attr_set = true;
+  }
+  const int items = p.B * 25 * p.H;
+  const int grid = items < num_sms ? items : num_sms;
+  window2_kernel<<<grid, W2_THREADS, W2_SMEM_BYTES, st>>>(tq, tkv, trel, tout, p);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+}  // namespace wm

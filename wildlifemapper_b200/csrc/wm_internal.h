@@ -62,5 +62,7 @@ struct WindowParams {
 };
 int window_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const WindowParams& p,
                     cudaStream_t st);
+int window2_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const CUtensorMap& tout,
+                     const WindowParams& p, int num_sms, cudaStream_t st);
 
 }  // namespace wm

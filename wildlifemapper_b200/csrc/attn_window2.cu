@@ -44,6 +44,25 @@ static_assert(W2_OFF_SCR % 1024 == 0 && W2_SCR_STRIDE % 1024 == 0, "staging alig
 constexpr int W2_COL_T = 196;   // T_h at S' columns 196..222, T_w at 223..249
 constexpr int W2_COL_O = 192;   // O_t (64 columns) over the consumed score / table columns
 
+// Rare path of the single-pass softmax, kept OUT OF LINE (it sat in the middle of every unrolled chunk before, tripled the
+// size of the hot loop and cost ~17 % of the softmax warps' time in instruction-fetch stalls): the reference maximum
+// of this row was raised by log2(1/alpha) -- rescale the P chunks already written for it.
+__device__ __noinline__ void window2_rescale_p(uint32_t p_addr, int nchunks, float alpha) {
+  tmem_st_wait();
+#pragma unroll 1
+  for (int kk = 0; kk < nchunks; ++kk) {
+    uint32_t o[16];
+    tmem_ld16(p_addr + kk * 16, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float lo = __uint_as_float(o[i] << 16) * alpha, hi = __uint_as_float(o[i] & 0xffff0000u) * alpha;
+      o[i] = pack_bf16(lo, hi);
+    }
+    tmem_st16(p_addr + kk * 16, o);
+  }
+}
+
 __global__ void __launch_bounds__(W2_THREADS, 1)
 window2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                const __grid_constant__ CUtensorMap tmap_rel, const __grid_constant__ CUtensorMap tmap_out,
@@ -233,63 +252,52 @@ window2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       // columns of bf16 pairs) overwrites score columns [16c, 16c+16), which chunk c/2 has already consumed.
       tmem_ld32(lane_addr, v[0]);
       tmem_ld_wait();
-      float m_ref = -INFINITY;
+      // reference maximum = exact maximum of the first 32 scores (cheap: no exp2), so the first chunk never needs a redo
+      float m_ref;
+      {
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          mx[i & 3] = fmaxf(mx[i & 3], fmaf(__uint_as_float(v[0][i]), c1, bh[i / 14] + bw[i % 14]));
+        m_ref = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      }
       float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int c = 0; c < 7; ++c) {
         uint32_t(&cur)[32] = v[c & 1];
         if (c < 6) tmem_ld32(lane_addr + (c + 1) * 32, v[(c + 1) & 1]);
-        constexpr int NV_FULL = 32;
-        const int nv = (c < 6) ? NV_FULL : 4;  // valid scores in this chunk (keys 192..195 in the last one)
+        const int nv = (c < 6) ? 32 : 4;  // valid scores in this chunk (keys 192..195 in the last one)
         float e[32];
-        float ymax[2] = {-INFINITY, -INFINITY};
-        float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < nv) {
-            const int k = c * 32 + i;          // key index (compile time): window row k / 14, column k % 14
-            const float yv = fmaf(__uint_as_float(cur[i]), c1, bh[k / 14] + bw[k % 14]);
-            ymax[i & 1] = fmaxf(ymax[i & 1], yv);
-            e[i] = ex2_approx(yv - m_ref);
-            cs[i & 3] += e[i];
-          } else {
-            e[i] = 0.0f;                       // pad keys 196..207
-          }
-        }
-        const float m_chunk = fmaxf(ymax[0], ymax[1]);
-        const bool need = m_chunk > m_ref + W2_TAU;  // always true for the first chunk
-        if (__any_sync(0xffffffffu, need)) {
-          const float m_new = need ? m_chunk : m_ref;
-          const float alpha = ex2_approx(m_ref - m_new);
-          if (c > 0) {  // P chunks of this row written against the old reference
-            tmem_st_wait();
-#pragma unroll
-            for (int kk = 0; kk < c; ++kk) {
-              uint32_t o[16];
-              tmem_ld16(lane_addr + kk * 16, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float lo = __uint_as_float(o[i] << 16) * alpha, hi2 = __uint_as_float(o[i] & 0xffff0000u) * alpha;
-                o[i] = pack_bf16(lo, hi2);
-              }
-              tmem_st16(lane_addr + kk * 16, o);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) ls[i] *= alpha;
-          }
-          m_ref = m_new;
+        float cs[4];
+#pragma unroll 1
+        for (int pass = 0;; ++pass) {  // one iteration unless the reference maximum has to be raised (rare)
+          float ymax[2] = {-INFINITY, -INFINITY};
 #pragma unroll
           for (int i = 0; i < 4; ++i) cs[i] = 0.0f;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (i < nv) {
-              const int k = c * 32 + i;
+              const int k = c * 32 + i;          // key index (compile time): window row k / 14, column k % 14
               const float yv = fmaf(__uint_as_float(cur[i]), c1, bh[k / 14] + bw[k % 14]);
+              ymax[i & 1] = fmaxf(ymax[i & 1], yv);
               e[i] = ex2_approx(yv - m_ref);
               cs[i & 3] += e[i];
+            } else {
+              e[i] = 0.0f;                       // pad keys 196..207
             }
           }
+          const float m_chunk = fmaxf(ymax[0], ymax[1]);
+          const bool need = m_chunk > m_ref + W2_TAU;
+          if (pass == 0 && __any_sync(0xffffffffu, need)) {
+            const float m_new = need ? m_chunk : m_ref;
+            const float alpha = ex2_approx(m_ref - m_new);
+            if (c > 0) window2_rescale_p(lane_addr, c, alpha);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ls[i] *= alpha;
+            m_ref = m_new;
+            continue;
+          }
+          break;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) ls[i] += cs[i];

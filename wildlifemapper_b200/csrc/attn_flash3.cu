@@ -342,7 +342,7 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       if (q4 == 0 && lane == 0) F3_TRACE(t, j, 1);
       if (TURNS) named_bar_sync(2 + t, 256);  // my turn on the MUFU
       if (q4 == 0 && lane == 0) F3_TRACE(t, j, 3);
-      float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // this tile's row sum (relative to m_ref), 4 independent chains
+      uint64_t ls2[2] = {0ull, 0ull};  // this tile's row sum (relative to m_ref): 2 packed pairs = 4 independent chains
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t(&cur)[32] = v[c & 1];
@@ -350,27 +350,33 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const float bh = (c < 2) ? bh0 : bh1;
         float d = RELPOS ? bh - m_ref : -m_ref;  // +inf while m_ref = -inf: the first chunk always takes the exact path
         float ymax[2] = {-INFINITY, -INFINITY};
-        float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        uint64_t cs2[2] = {0ull, 0ull};  // 2 x 2 partial row sums (packed fp32x2: FFMA2 / FADD2 halve the FMA-pipe issue load)
         uint32_t pk[16];
+        const uint64_t c1p = pk2(c1, c1);
+        {
+          const uint64_t dp = pk2(d, d);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float y0, y1;
-          if (RELPOS) {
-            y0 = fmaf(__uint_as_float(cur[2 * i]), c1, tw[RELPOS ? (c & 1) * 32 + 2 * i : 0]);
-            y1 = fmaf(__uint_as_float(cur[2 * i + 1]), c1, tw[RELPOS ? (c & 1) * 32 + 2 * i + 1 : 0]);
-            ymax[0] = fmaxf(ymax[0], y0);
-            ymax[1] = fmaxf(ymax[1], y1);
-            y0 += d;
-            y1 += d;
-          } else {
-            ymax[0] = fmaxf(ymax[0], __uint_as_float(cur[2 * i]));  // raw scores: c1 > 0
-            ymax[1] = fmaxf(ymax[1], __uint_as_float(cur[2 * i + 1]));
-            y0 = fmaf(__uint_as_float(cur[2 * i]), c1, d);
-            y1 = fmaf(__uint_as_float(cur[2 * i + 1]), c1, d);
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t vp = pk2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1]));
+            uint64_t yp;
+            if (RELPOS) {
+              const uint64_t y2 = fma2(vp, c1p, pk2(tw[RELPOS ? (c & 1) * 32 + 2 * i : 0], tw[RELPOS ? (c & 1) * 32 + 2 * i + 1 : 0]));
+              float y0, y1;
+              unpk2(y2, y0, y1);
+              ymax[0] = fmaxf(ymax[0], y0);
+              ymax[1] = fmaxf(ymax[1], y1);
+              yp = add2(y2, dp);
+            } else {
+              ymax[0] = fmaxf(ymax[0], __uint_as_float(cur[2 * i]));  // raw scores: c1 > 0
+              ymax[1] = fmaxf(ymax[1], __uint_as_float(cur[2 * i + 1]));
+              yp = fma2(vp, c1p, dp);
+            }
+            float a0, a1;
+            unpk2(yp, a0, a1);
+            const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+            cs2[i & 1] = add2(cs2[i & 1], pk2(e0, e1));
+            pk[i] = pack_bf16(e0, e1);
           }
-          const float e0 = ex2_approx(y0), e1 = ex2_approx(y1);
-          cs[i & 3] += e0 + e1;
-          pk[i] = pack_bf16(e0, e1);
         }
         const float m_chunk = RELPOS ? fmaxf(ymax[0], ymax[1]) + bh : fmaxf(ymax[0], ymax[1]) * c1;
         const bool need = m_chunk > m_ref + F3_TAU;
@@ -405,36 +411,43 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
               }
               tmem_st16(s_addr + k * 16, o);
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) ls[i] *= alpha;
+            const uint64_t ap = pk2(alpha, alpha);
+            ls2[0] = mul2(ls2[0], ap);
+            ls2[1] = mul2(ls2[1], ap);
           }
           m_ref = m_new;
           d = RELPOS ? bh - m_ref : -m_ref;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) cs[i] = 0.0f;
+          cs2[0] = 0ull;
+          cs2[1] = 0ull;
+          const uint64_t dp = pk2(d, d);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float y0, y1;
-            if (RELPOS) {
-              y0 = fmaf(__uint_as_float(cur[2 * i]), c1, tw[RELPOS ? (c & 1) * 32 + 2 * i : 0]) + d;
-              y1 = fmaf(__uint_as_float(cur[2 * i + 1]), c1, tw[RELPOS ? (c & 1) * 32 + 2 * i + 1 : 0]) + d;
-            } else {
-              y0 = fmaf(__uint_as_float(cur[2 * i]), c1, d);
-              y1 = fmaf(__uint_as_float(cur[2 * i + 1]), c1, d);
-            }
-            const float e0 = ex2_approx(y0), e1 = ex2_approx(y1);
-            cs[i & 3] += e0 + e1;
+            const uint64_t vp = pk2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1]));
+            uint64_t yp;
+            if (RELPOS)
+              yp = add2(fma2(vp, c1p, pk2(tw[RELPOS ? (c & 1) * 32 + 2 * i : 0], tw[RELPOS ? (c & 1) * 32 + 2 * i + 1 : 0])), dp);
+            else
+              yp = fma2(vp, c1p, dp);
+            float a0, a1;
+            unpk2(yp, a0, a1);
+            const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+            cs2[i & 1] = add2(cs2[i & 1], pk2(e0, e1));
             pk[i] = pack_bf16(e0, e1);
           }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ls[i] += cs[i];
+        ls2[0] = add2(ls2[0], cs2[0]);
+        ls2[1] = add2(ls2[1], cs2[1]);
         tmem_st16(s_addr + c * 16, pk);
         if (c < 3) tmem_ld_wait();  // chunk c + 1 has landed
       }
       if (q4 == 0 && lane == 0) F3_TRACE(t, j, 4);
       if (TURNS && (t == 0 || j + 1 < nk)) named_bar_arrive(3 - t, 256);  // hand the MUFU to the other tile
-      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      {
+        float s0, s1, s2, s3;
+        unpk2(ls2[0], s0, s1);
+        unpk2(ls2[1], s2, s3);
+        l_run += (s0 + s1) + (s2 + s3);
+      }
       tmem_st_wait();
       if (q4 == 0 && lane == 0) F3_TRACE(t, j, 5);
       tc_fence_before();

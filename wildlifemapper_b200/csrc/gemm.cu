@@ -69,22 +69,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// Two GELUs at once on the packed fp32x2 FMA path of sm_100 (FFMA2 / FMUL2: one issue slot per pair)
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
+// Two GELUs at once on the packed fp32x2 FMA path of sm_100 (FFMA2 / FMUL2: one issue slot per pair; common.cuh)
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   const float z0 = fminf(fmaxf(x0 * 0.70710678118654752f, -3.0f), 3.0f);
   const float z1 = fminf(fmaxf(x1 * 0.70710678118654752f, -3.0f), 3.0f);
@@ -100,7 +85,7 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   pl = fma2(pl, z2, pk2(1.1282684803009033f, 1.1282684803009033f));
   const uint64_t hx = mul2(pk2(x0, x1), pk2(0.5f, 0.5f));
   const uint64_t r = fma2(hx, mul2(pl, z), hx);
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(r));
+  unpk2(r, x0, x1);
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {

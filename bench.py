@@ -229,10 +229,29 @@ def run_b200(args):
     launches = (enc_eng.launches + dec_eng.launches - l0) + 2 * args.steps  # + postprocess + batched NMS
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- end to end (`e2e`): pinned host tiles -> H2D -> path -> D2H of the packed detections, every step
+    # ---- end to end (`e2e`): pinned host tiles -> H2D -> path -> D2H of the packed detections, every step.  The tile
+    # feed is double buffered: the H2D copy of step i+1 runs on a copy stream while step i computes (what a serving
+    # loop does); every step still pays one full H2D of its own inputs and one D2H of its own detections inside the
+    # timed region, and the caller synchronises on each step's detections.
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_buf = [torch.empty_like(dev_tiles), torch.empty_like(dev_tiles)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"i": 0}
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])  # the step that last read this buffer has finished
+            dev_buf[slot].copy_(host_tiles, non_blocking=True)
+            ready[slot].record(copy_stream)
+
     def e2e_step():
-        t = host_tiles.to(dev, non_blocking=True)
-        packed, counts, keep_idx, keep_cnt = step(t)
+        slot = state["i"] & 1
+        state["i"] += 1
+        prefetch(slot ^ 1)  # next step's tiles (the very first call copies its own tiles below)
+        torch.cuda.current_stream().wait_event(ready[slot])
+        packed, counts, keep_idx, keep_cnt = step(dev_buf[slot])
+        consumed[slot].record()
         nloc = B  # every rank reads back its own shard's detections
         host_out.copy_(packed[rank * nloc:(rank + 1) * nloc] if world > 1 else packed, non_blocking=True)
         host_cnt.copy_(counts[rank * nloc:(rank + 1) * nloc] if world > 1 else counts, non_blocking=True)
@@ -240,8 +259,12 @@ def run_b200(args):
         host_kcnt.copy_(keep_cnt[rank * nloc:(rank + 1) * nloc] if world > 1 else keep_cnt, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller consumes the detections of this step
 
+    for s_ in (0, 1):
+        consumed[s_].record()
+    prefetch(0)
     e2e_step()
     ms_e2e = timed(args.steps, e2e_step)
+    torch.cuda.synchronize()
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = host_tiles.numel() * 4
     d2h = host_out.numel() * 4 + host_cnt.numel() * 4 + host_keep.numel() * 4 + host_kcnt.numel() * 4

@@ -24,9 +24,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "wildlifemapper_b200"))
 
 MODEL_CONFIGS = {"vit_b": (768, 12, 12, (2, 5, 8, 11)), "vit_l": (1024, 24, 16, (5, 11, 17, 23)),
-                 "vit_t": (128, 2, 2, (1,))}
+                 "vit_h": (1280, 32, 16, (7, 15, 23, 31)), "vit_t": (128, 2, 2, (1,))}
 # algorithmic GFLOP per tile (SURVEY.md section 8d / BASELINE.md section 3)
-GFLOP_PER_TILE = {"vit_b": 1085.0, "vit_l": 2988.7}
+GFLOP_PER_TILE = {"vit_b": 1085.0, "vit_l": 2988.7, "vit_h": 5797.8}
 METRIC = "tiles_per_sec"
 UNIT = "tiles/s"
 

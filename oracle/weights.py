@@ -26,6 +26,8 @@ MODEL_CONFIGS = {
     "vit_h": (1280, 32, 16, (7, 15, 23, 31)),
     # tiny config for fast CPU tests (not a reference model; same structure)
     "vit_t": (128, 2, 2, (1,)),
+    # same, with ViT-H's head dim 80 (8 heads x 80): exercises the head-dim-80 attention kernels
+    "vit_t80": (640, 2, 8, (1,)),
 }
 
 HFC_DIM = 1024

@@ -86,7 +86,7 @@ def test_conv3x3_matches_conv2d():
 
 
 # ------------------------------------------------------------------ bandwidth kernels
-@pytest.mark.parametrize("D", [128, 256, 768, 1024, 1280])
+@pytest.mark.parametrize("D", [128, 256, 640, 768, 1024, 1280])
 def test_layernorm(D):
     rows = 1000
     x = rnd(rows, D, seed=11, scale=3.0, dtype=torch.float32) + 0.5
@@ -168,8 +168,10 @@ def test_attn_small(Tq, Tk, hd, H):
     assert (out.float() - ref).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize("hd,H,T", [(64, 2, 256), (64, 3, 4096), (128, 2, 512), (128, 8, 4096)])
+@pytest.mark.parametrize("hd,H,T", [(64, 2, 256), (64, 3, 4096), (128, 2, 512), (128, 8, 4096), (80, 3, 1024)])
 def test_attn_flash_plain(hd, H, T, flash_version):
+    if hd == 80 and flash_version != 3:
+        pytest.skip("head dim 80 (ViT-H) is served by the v3 kernel only")
     B = 2 if T <= 512 else 1
     q = rnd(B * T, H * hd, seed=24)
     kv = rnd(B * T, 2 * H * hd, seed=25)
@@ -221,12 +223,15 @@ def relpos_bias(q, rel_h, rel_w, S):
     return (bh[..., :, None] + bw[..., None, :]).reshape(B, H, T, T)
 
 
-def test_attn_flash_global_relpos(flash_version):
-    B, H, hd, T = 2, 3, 64, 4096
+@pytest.mark.parametrize("hd", [64, 80])
+def test_attn_flash_global_relpos(flash_version, hd):
+    if hd == 80 and flash_version != 3:
+        pytest.skip("head dim 80 (ViT-H) is served by the v3 kernel only")
+    B, H, T = 2, 3, 4096
     D = H * hd
     qkv = rnd(B * T, 3 * D, seed=26)
     rel_h, rel_w = rnd(127, hd, seed=27, scale=0.3), rnd(127, hd, seed=28, scale=0.3)
-    table = torch.zeros(256, 64, device=DEV, dtype=torch.bfloat16)
+    table = torch.zeros(256, hd, device=DEV, dtype=torch.bfloat16)
     table[:127], table[128:255] = rel_h, rel_w
     out = torch.zeros(B * T, D, device=DEV, dtype=torch.bfloat16)
     scale = hd ** -0.5
@@ -246,13 +251,13 @@ def window_version(request):
     lib.call("wm_set_option", b"window_version", 2)
 
 
-@pytest.mark.parametrize("B,H", [(1, 2), (2, 12), (3, 5)])
-def test_attn_window(B, H, window_version):
-    hd, S = 64, 14
+@pytest.mark.parametrize("B,H,hd", [(1, 2, 64), (2, 12, 64), (3, 5, 64), (2, 4, 80)])
+def test_attn_window(B, H, hd, window_version):
+    S = 14
     D = H * hd
     qkv = rnd(B, 64, 64, 3 * D, seed=29)
     rel_h, rel_w = rnd(27, hd, seed=30, scale=0.3), rnd(27, hd, seed=31, scale=0.3)
-    table = torch.zeros(64, 64, device=DEV, dtype=torch.bfloat16)
+    table = torch.zeros(64, hd, device=DEV, dtype=torch.bfloat16)
     table[:27], table[32:59] = rel_h, rel_w
     out = torch.zeros(B, 64, 64, D, device=DEV, dtype=torch.bfloat16)
     scale = hd ** -0.5

@@ -64,6 +64,17 @@ def test_tiny_model_vs_reference_golden(golden_dir, tag, batch, nq):
     check_outputs(out, g["pred_logits"], g["pred_boxes"], tag)
 
 
+def test_head_dim_80_model_vs_oracle():
+    """ViT-H's head dim (80) on a 2-block encoder (one windowed, one global block): the sm_100a path against the fp32
+    CPU oracle on the same seeded weights and tiles (the oracle itself is pinned to the reference for vit_t / vit_b)."""
+    model = build("vit_t80", 51)
+    tiles = make_tiles(2, seed=2)
+    with torch.no_grad():
+        out = model(NestedTensor(tiles.to(DEV), None), None)
+    ref = om.forward(make_state_dict("vit_t80", seed=0), "vit_t80", tiles)
+    check_outputs(out, ref["pred_logits"].numpy(), ref["pred_boxes"].numpy(), "vit_t80")
+
+
 def test_vit_b_vs_reference_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "golden_model_vit_b.npz"))
     sam, _crit, post = sa.sam_model_registry["vit_b"]()

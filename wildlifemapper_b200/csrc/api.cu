@@ -274,7 +274,8 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
                   int64_t v_width, int64_t ldv, int v_col0, const void* rel_table, void* out_bf16, int64_t ldo, int B,
                   int H, int Tq, int Tk, int hd, float scale, void* stream) {
   if (int rc = ensure_device()) return rc;
-  if (B <= 0 || H <= 0 || (hd != 64 && hd != 128)) return fail(WM_ERR_SHAPE, "wm_attn_flash: bad B/H/hd");
+  if (B <= 0 || H <= 0 || (hd != 64 && hd != 80 && hd != 128)) return fail(WM_ERR_SHAPE, "wm_attn_flash: head dim must be 64, 80 or 128");
+  if (hd == 80 && (g_flash_version != 3 || Tq % 256 != 0)) return fail(WM_ERR_SHAPE, "wm_attn_flash: head dim 80 needs the v3 kernel (Tq %% 256 == 0)");
   if (Tq % 128 || Tk % 128 || Tk < 128) return fail(WM_ERR_SHAPE, "wm_attn_flash: Tq, Tk must be multiples of 128");
   if ((int64_t)B * Tq > q_rows || (int64_t)B * Tk > k_rows || (int64_t)B * Tk > v_rows) return fail(WM_ERR_SHAPE, "wm_attn_flash: rows");
   if (q_col0 + H * hd > q_width || k_col0 + H * hd > k_width || v_col0 + H * hd > v_width) return fail(WM_ERR_SHAPE, "wm_attn_flash: columns");
@@ -289,8 +290,9 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   if (int rc = make_map_2d(&tv, v, (uint64_t)v_rows, (uint64_t)v_width, (uint64_t)ldv, kv_box, "wm_attn_flash(v)")) return rc;
   trel = tq;
   if (rel_table != nullptr) {
-    if (hd != 64 || Tq != 4096 || Tk != 4096) return fail(WM_ERR_SHAPE, "wm_attn_flash: rel-pos needs hd=64, 64x64 tokens");
-    if (int rc = make_map_2d(&trel, rel_table, 256, 64, 64, (v2 || v3) ? 16 : 256, "wm_attn_flash(rel)")) return rc;
+    if ((hd != 64 && !(hd == 80 && v3)) || Tq != 4096 || Tk != 4096)
+      return fail(WM_ERR_SHAPE, "wm_attn_flash: rel-pos needs hd 64 (or 80 on the v3 kernel) and 64x64 tokens");
+    if (int rc = make_map_2d(&trel, rel_table, 256, (uint64_t)hd, (uint64_t)hd, (v2 || v3) ? 16 : 256, "wm_attn_flash(rel)")) return rc;
   }
   wm::FlashParams p{};
   p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.scale = scale;
@@ -312,7 +314,9 @@ int wm_debug_flash_trace(uint64_t* host_out_3x64x4) {
 int wm_attn_window(const void* qkv, const void* rel_table, void* out_bf16, int B, int H, int D, float scale,
                    void* stream) {
   if (int rc = ensure_device()) return rc;
-  if (B <= 0 || B > 65535 || H <= 0 || D != H * 64) return fail(WM_ERR_SHAPE, "wm_attn_window: needs D == H*64 (hd = 64)");
+  if (B <= 0 || B > 65535 || H <= 0 || D % H != 0) return fail(WM_ERR_SHAPE, "wm_attn_window: bad B / H / D");
+  const int hd = D / H;
+  if (hd != 64 && hd != 80) return fail(WM_ERR_SHAPE, "wm_attn_window: head dim must be 64 or 80");
   if (!aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_attn_window: alignment");
   CUtensorMap tq, tkv, trel, tout;
   const uint64_t W3 = (uint64_t)3 * D;
@@ -321,7 +325,7 @@ int wm_attn_window(const void* qkv, const void* rel_table, void* out_bf16, int B
   wm::WindowParams p{};
   p.B = B; p.H = H; p.scale = scale; p.D = D;
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  if (g_window_version == 2) {
+  if (g_window_version == 2 && hd == 64) {
     // dense 14-wide boxes: a query half is 7 window rows x 14, K / V are the whole 14 x 14 window; zero padding of the
     // 70x70 grid = TMA out-of-bounds fill on loads, the crop back to 64x64 = TMA bounds check on the output store
     const uint32_t box_q[4] = {64, 14, 7, 1};
@@ -341,8 +345,8 @@ int wm_attn_window(const void* qkv, const void* rel_table, void* out_bf16, int B
   const uint32_t box_kv[4] = {64, 16, 14, 1};
   if (int rc = make_map(&tq, qkv, 4, dims, strides, box_q, "wm_attn_window(q)")) return rc;
   if (int rc = make_map(&tkv, qkv, 4, dims, strides, box_kv, "wm_attn_window(kv)")) return rc;
-  if (int rc = make_map_2d(&trel, rel_table, 64, 64, 64, 64, "wm_attn_window(rel)")) return rc;
-  return check_launch(wm::window_dispatch(tq, tkv, trel, p, (cudaStream_t)stream), "wm_attn_window");
+  if (int rc = make_map_2d(&trel, rel_table, 64, (uint64_t)hd, (uint64_t)hd, 64, "wm_attn_window(rel)")) return rc;
+  return check_launch(wm::window_dispatch(tq, tkv, trel, p, hd, (cudaStream_t)stream), "wm_attn_window");
 }
 
 int wm_attn_small(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out_bf16,

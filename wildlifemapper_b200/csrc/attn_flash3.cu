@@ -48,26 +48,33 @@ __device__ unsigned long long g_f3_trace[3][64][8];
 template <int HD, bool RELPOS>
 struct Flash3Cfg {
   static_assert(HD % 16 == 0 && HD >= 64 && HD <= 128, "head dim");
-  static_assert(!RELPOS || HD == 64, "rel-pos variant: head dim 64");
-  static constexpr int SUB = (HD + 63) / 64;       // 64-column (128-byte) sub-tiles per operand row
+  static_assert(!RELPOS || HD <= 96, "rel-pos variant: tensor-memory budget");
+  static constexpr int SUB = (HD + 63) / 64;       // 64-column (128-byte) sub-tiles per operand row (a partial second
+                                                   // sub-tile -- head dim 80 -- is loaded 64 wide; only HD columns are used)
   static constexpr int KSTEPS = HD / 16;           // K = 16 MMA steps over the head dim
   static constexpr int STAGES = (SUB == 1) ? 4 : 2;
   static constexpr int TILE_BYTES = SUB * 16384;   // 128 rows (queries or keys) x SUB x 128 B
   static constexpr int OFF_Q = 0;                  // 2 query tiles
   static constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * TILE_BYTES;
-  static constexpr int OFF_TAB = OFF_V + STAGES * TILE_BYTES;
-  // RELPOS prologue: Rw [128 rows] + 2 x Rh slice [80 rows]; afterwards the first 32 KB are fp32 scatter scratch
-  static constexpr int TAB_BYTES = RELPOS ? (16384 + 2 * 10240) : 0;
-  static constexpr int OFF_BAR = OFF_TAB + TAB_BYTES;
+  // RELPOS prologue: Rw [128 rows] + 2 x Rh slice [80 rows] (x SUB sub-tiles); afterwards its first 32 KB are fp32
+  // scatter scratch.  Head dim 64: own region.  Larger head dims: the tables ALIAS K stage 1 and the V stages, whose
+  // first loads wait for the prologue (t_done).
+  static constexpr bool TAB_ALIAS = RELPOS && SUB > 1;
+  static constexpr int TAB_BYTES = RELPOS ? SUB * (16384 + 2 * 10240) : 0;
+  static constexpr int OFF_TAB = TAB_ALIAS ? OFF_K + TILE_BYTES : OFF_V + STAGES * TILE_BYTES;
+  static_assert(!TAB_ALIAS || TAB_BYTES <= (2 * STAGES - 1) * TILE_BYTES, "aliased table region");
+  static constexpr int OFF_BAR = OFF_V + STAGES * TILE_BYTES + (TAB_ALIAS ? 0 : TAB_BYTES);
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  // TMEM columns: S_t at 128 t (P_t = bf16 pairs in its first 64 columns), O_t at 256 + HD t,
-  // RELPOS: T_h(t) columns 0..63 at 384 + 64 t (resident), prologue scratch in the S / O columns
+  // TMEM columns: S_t at 128 t (P_t = bf16 pairs in its first 64 columns), O_t at 256 + HD t, then the resident T_h:
+  //   head dim 64: fp32, 64 columns per tile (+ column 64 in a register);  larger: fp16 pairs, 33 of 40 columns per tile
   static constexpr int COL_O = 256;
-  static constexpr int COL_TH = 384;
+  static constexpr int COL_TH = COL_O + 2 * HD;
+  static constexpr bool TH_PACKED = HD > 64;
+  static constexpr int TH_STRIDE = TH_PACKED ? 40 : 64;
   static constexpr int TMEM_COLS = 512;
-  static_assert(COL_O + 2 * HD <= (RELPOS ? COL_TH : 512), "TMEM budget");
+  static_assert(COL_TH + (RELPOS ? 2 * TH_STRIDE : 0) <= 512, "TMEM budget");
 };
 
 template <int HD, bool RELPOS, bool TURNS>
@@ -137,17 +144,22 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             tma_load_2d(smem + Cfg::OFF_Q + t * Cfg::TILE_BYTES + s * 16384, &tmap_q, q_full, p.q_col0 + h * HD + s * 64,
                         b * p.Tq + m0 + t * 128);
         if (RELPOS) {
-          // table tensor [256,64]: rows 0..126 rel_pos_h, 128..254 rel_pos_w.  Box = 16 rows.
+          // table tensor [256,HD]: rows 0..126 rel_pos_h, 128..254 rel_pos_w.  Box = 64 columns x 16 rows.
           const int qi0 = m0 >> 6;  // first image row of this CTA (4 rows: 2 per query tile)
-          for (int i = 0; i < 8; ++i) tma_load_2d(smem + Cfg::OFF_TAB + i * 2048, &tmap_rel, q_full, 0, 128 + 16 * i);
-          for (int t = 0; t < 2; ++t)
-            for (int i = 0; i < 5; ++i)
-              tma_load_2d(smem + Cfg::OFF_TAB + 16384 + t * 10240 + i * 2048, &tmap_rel, q_full, 0, qi0 + 2 * t + 16 * i);
+          for (int sb = 0; sb < Cfg::SUB; ++sb) {
+            for (int i = 0; i < 8; ++i)
+              tma_load_2d(smem + Cfg::OFF_TAB + sb * 16384 + i * 2048, &tmap_rel, q_full, sb * 64, 128 + 16 * i);
+            for (int t = 0; t < 2; ++t)
+              for (int i = 0; i < 5; ++i)
+                tma_load_2d(smem + Cfg::OFF_TAB + Cfg::SUB * 16384 + (t * Cfg::SUB + sb) * 10240 + i * 2048, &tmap_rel, q_full,
+                            sb * 64, qi0 + 2 * t + 16 * i);
+          }
         }
       }
       int st = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nk; ++j) {
+        if (Cfg::TAB_ALIAS && j == 1) mbar_wait(t_done, 0);  // K stage 1 and the V stages hold the tables until then
         mbar_wait(&k_empty[st], ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
@@ -156,6 +168,7 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             tma_load_2d(smem + Cfg::OFF_K + st * Cfg::TILE_BYTES + s * 16384, &tmap_k, &k_full[st],
                         p.k_col0 + h * HD + s * 64, b * p.Tk + j * 128);
         }
+        if (Cfg::TAB_ALIAS && j == 0) mbar_wait(t_done, 0);
         mbar_wait(&v_empty[st], ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
@@ -177,21 +190,26 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       tc_fence_after();
       if (RELPOS) {
         constexpr uint32_t idesc_tw = make_idesc_bf16(128, 128, 0, 0);
-        constexpr uint32_t idesc_th = make_idesc_bf16(128, 64, 0, 0);
+        constexpr uint32_t idesc_th = make_idesc_bf16(128, Cfg::TH_PACKED ? 80 : 64, 0, 0);
         constexpr uint32_t idesc_tx = make_idesc_bf16(128, 16, 0, 0);
         const uint32_t stab = smem_u32(smem + Cfg::OFF_TAB);
-        // T_w(t) -> S_t columns; T_h(t)[0..63] -> resident columns; T_h(t)[64..79] -> scratch in the O columns
+        // T_w(t) -> S_t columns.  Head dim 64: T_h(t)[0..63] -> resident columns, T_h(t)[64..79] -> scratch in the O
+        // columns.  Larger head dims: T_h(t)[0..79] -> O_t columns (scratch; the softmax warps repack it as fp16 pairs).
         if (leader) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            const uint32_t srh = stab + 16384 + t * 10240;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ad = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES + ks * 32, 16, 1024);
-              umma_bf16(tmem_base + t * 128, ad, make_sdesc_sw128(stab + ks * 32, 16, 1024), idesc_tw, ks != 0);
-              umma_bf16(tmem_base + Cfg::COL_TH + t * 64, ad, make_sdesc_sw128(srh + ks * 32, 16, 1024), idesc_th, ks != 0);
-              umma_bf16(tmem_base + Cfg::COL_O + t * 16, ad, make_sdesc_sw128(srh + 8192 + ks * 32, 16, 1024), idesc_tx,
-                        ks != 0);
+            for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+              const uint32_t koff = (ks & 3) * 32;
+              const uint32_t srh = stab + Cfg::SUB * 16384 + (t * Cfg::SUB + (ks >> 2)) * 10240 + koff;
+              const uint64_t ad = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES + (ks >> 2) * 16384 + koff, 16, 1024);
+              umma_bf16(tmem_base + t * 128, ad, make_sdesc_sw128(stab + (ks >> 2) * 16384 + koff, 16, 1024), idesc_tw, ks != 0);
+              if (Cfg::TH_PACKED) {
+                umma_bf16(tmem_base + Cfg::COL_O + t * HD, ad, make_sdesc_sw128(srh, 16, 1024), idesc_th, ks != 0);
+              } else {
+                umma_bf16(tmem_base + Cfg::COL_TH + t * 64, ad, make_sdesc_sw128(srh, 16, 1024), idesc_th, ks != 0);
+                umma_bf16(tmem_base + Cfg::COL_O + t * 16, ad, make_sdesc_sw128(srh + 8192, 16, 1024), idesc_tx, ks != 0);
+              }
             }
           }
           umma_commit(t_full);
@@ -275,13 +293,29 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     float tw[RELPOS ? 64 : 1];
     float bh64 = 0.0f;                                            // T_h column 64 (only needed by key row 0)
     const int hi = r >> 6;                                        // image row of this query inside the tile (warp-uniform)
-    const uint32_t th_addr = lane_addr + Cfg::COL_TH + t * 64;    // bias_h[kh] = T_h[hi + 63 - kh]
+    const uint32_t th_addr = lane_addr + Cfg::COL_TH + t * Cfg::TH_STRIDE;  // bias_h[kh] = T_h[hi + 63 - kh]
 
     if (RELPOS) {
       const int qj = (m0 + t * 128 + r) & 63;
       mbar_wait(t_full, 0);
       tc_fence_after();
-      {
+      if (Cfg::TH_PACKED) {
+        // T_h(t)[0..79] sits in the O_t columns as fp32: keep [0..64] as fp16 pairs (x log2 e) in the resident columns
+        uint32_t a[32], bq[32], cq[16];
+        tmem_ld32(o_addr, a);
+        tmem_ld32(o_addr + 32, bq);
+        tmem_ld16(o_addr + 64, cq);
+        tmem_ld_wait();
+        uint32_t pkh[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          pkh[i] = pack_f16(__uint_as_float(a[2 * i]) * F3_LOG2E, __uint_as_float(a[2 * i + 1]) * F3_LOG2E);
+          pkh[16 + i] = pack_f16(__uint_as_float(bq[2 * i]) * F3_LOG2E, __uint_as_float(bq[2 * i + 1]) * F3_LOG2E);
+        }
+        tmem_st32(th_addr, pkh);
+        tmem_st1(th_addr + 32, pack_f16(__uint_as_float(cq[0]) * F3_LOG2E, 0.0f));
+        tmem_st_wait();
+      } else {
         const uint32_t x = tmem_ld1(lane_addr + Cfg::COL_O + t * 16);
         tmem_ld_wait();
         bh64 = __uint_as_float(x) * F3_LOG2E;
@@ -330,12 +364,20 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       tmem_ld32(s_addr, v[0]);
       float bh0 = 0.0f, bh1 = 0.0f;
       if (RELPOS) {
-        const int c0 = hi + 63 - 2 * j;  // column of key row 2j; key row 2j+1 is column c0 - 1 (>= 0)
-        const uint32_t a0 = tmem_ld1(th_addr + (c0 > 63 ? 63 : c0));
-        const uint32_t a1 = tmem_ld1(th_addr + c0 - 1);
-        tmem_ld_wait();
-        bh0 = (c0 > 63) ? bh64 : __uint_as_float(a0) * F3_LOG2E;
-        bh1 = __uint_as_float(a1) * F3_LOG2E;
+        const int c0 = hi + 63 - 2 * j;  // T_h index of key row 2j; key row 2j+1 is index c0 - 1 (>= 0)
+        if (Cfg::TH_PACKED) {
+          const uint32_t a0 = tmem_ld1(th_addr + (c0 >> 1));
+          const uint32_t a1 = tmem_ld1(th_addr + ((c0 - 1) >> 1));
+          tmem_ld_wait();
+          bh0 = unpack_f16(a0, c0 & 1);
+          bh1 = unpack_f16(a1, (c0 - 1) & 1);
+        } else {
+          const uint32_t a0 = tmem_ld1(th_addr + (c0 > 63 ? 63 : c0));
+          const uint32_t a1 = tmem_ld1(th_addr + c0 - 1);
+          tmem_ld_wait();
+          bh0 = (c0 > 63) ? bh64 : __uint_as_float(a0) * F3_LOG2E;
+          bh1 = __uint_as_float(a1) * F3_LOG2E;
+        }
       } else {
         tmem_ld_wait();
       }
@@ -504,9 +546,13 @@ int flash3_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
   if (p.Tq % 256 != 0 || p.Tk % 128 != 0 || p.Tk < 128) return WM_ERR_SHAPE;
   const bool turns = p.turns != 0;
   if (p.use_relpos) {
-    if (hd != 64 || p.Tq != 4096 || p.Tk != 4096) return WM_ERR_SHAPE;
-    return turns ? launch_flash3<64, true, true>(tq, tk, tv, trel, p, st) : launch_flash3<64, true, false>(tq, tk, tv, trel, p, st);
+    if (p.Tq != 4096 || p.Tk != 4096) return WM_ERR_SHAPE;
+    if (hd == 64)
+      return turns ? launch_flash3<64, true, true>(tq, tk, tv, trel, p, st) : launch_flash3<64, true, false>(tq, tk, tv, trel, p, st);
+    if (hd == 80) return launch_flash3<80, true, true>(tq, tk, tv, trel, p, st);
+    return WM_ERR_SHAPE;
   }
+  if (hd == 80) return launch_flash3<80, false, true>(tq, tk, tv, trel, p, st);
   if (hd == 64)
     return turns ? launch_flash3<64, false, true>(tq, tk, tv, trel, p, st) : launch_flash3<64, false, false>(tq, tk, tv, trel, p, st);
   if (hd == 128)

@@ -21,25 +21,39 @@
 
 namespace wm {
 
+// (First-generation kernel: kept as the A/B reference for head dim 64 -- "window_version" 1 -- and as the path for head
+// dim 80 (ViT-H), whose operand tiles do not fit the double-buffered layout of attn_window2.cu.  The probabilities are
+// written back into the consumed score columns of tensor memory and P V reads its A operand from TMEM.)
 constexpr int WA_THREADS = 192;
-constexpr int WA_OFF_Q = 0;                      // 128 rows x 128 B (112 loaded)
-constexpr int WA_OFF_K = 16384;                  // 224 rows x 128 B
-constexpr int WA_OFF_V = WA_OFF_K + 28672;
-constexpr int WA_OFF_P = WA_OFF_V + 28672;       // 4 sub-tiles of 128 rows x 64 keys
-constexpr int WA_OFF_REL = WA_OFF_P + 65536;     // 64 rows x 128 B
-constexpr int WA_OFF_T = WA_OFF_REL + 8192;      // fp32 [128][65] scratch
 constexpr int WA_T_LD = 65;
-constexpr int WA_OFF_BAR = WA_OFF_T + 128 * WA_T_LD * 4;
-constexpr int WA_SMEM_BYTES = WA_OFF_BAR + 128 + 1024;
-constexpr int WA_COL_S = 0, WA_COL_T = 256, WA_COL_O = 320;
 constexpr float WA_LOG2E = 1.4426950408889634f;
 
+template <int HD>
+struct WinCfg {
+  static_assert(HD == 64 || HD == 80, "head dim");
+  static constexpr int SUB = (HD + 63) / 64;        // 64-column sub-tiles (a partial second one is loaded 64 wide)
+  static constexpr int KSTEPS = HD / 16;
+  static constexpr int Q_SUB = 16384;                // 128 rows x 128 B (112 loaded)
+  static constexpr int KV_SUB = 28672;               // 224 rows x 128 B
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + SUB * Q_SUB;
+  static constexpr int OFF_V = OFF_K + SUB * KV_SUB;
+  static constexpr int OFF_REL = OFF_V + SUB * KV_SUB;  // 64 table rows x 128 B per sub-tile
+  static constexpr int OFF_T = OFF_REL + SUB * 8192;    // fp32 [128][65] scratch
+  static constexpr int OFF_BAR = OFF_T + 128 * WA_T_LD * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static constexpr int COL_S = 0, COL_T = 256, COL_O = 320;  // P: bf16 pairs over S columns [0, 112)
+};
+
+template <int HD>
 __global__ void __launch_bounds__(WA_THREADS, 1)
 window_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                    const __grid_constant__ CUtensorMap tmap_rel, const WindowParams p) {
+  using Cfg = WinCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WA_OFF_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* bar_qk = bars + 0;
   uint64_t* bar_v = bars + 1;
   uint64_t* s_full = bars + 2;
@@ -47,15 +61,15 @@ window_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* o_full = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int mt = blockIdx.x;                 // which 7-row half of the window
   const int win = blockIdx.y / p.H, h = blockIdx.y % p.H;
   const int wy = win / 5, wx = win % 5;
   const int b = blockIdx.z;
 
-  // rows 112..127 of the Q tile are never loaded: zero them so the unused MMA rows stay finite
-  for (int i = threadIdx.x; i < (16384 - 14336) / 16; i += WA_THREADS)
-    reinterpret_cast<uint4*>(smem + WA_OFF_Q + 14336)[i] = make_uint4(0, 0, 0, 0);
+  // rows 112..127 of the Q sub-tiles are never loaded: zero them so the unused MMA rows stay finite
+  for (int i = threadIdx.x; i < Cfg::SUB * ((16384 - 14336) / 16); i += WA_THREADS)
+    reinterpret_cast<uint4*>(smem + Cfg::OFF_Q + (i / 128) * Cfg::Q_SUB + 14336)[i % 128] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -75,42 +89,53 @@ window_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bar_qk, 14336 + 28672 + 8192);
-      tma_load_4d(smem + WA_OFF_Q, &tmap_q, bar_qk, h * 64, wx * 14, wy * 14 + mt * 7, b);
-      tma_load_4d(smem + WA_OFF_K, &tmap_kv, bar_qk, p.D + h * 64, wx * 14, wy * 14, b);
-      tma_load_2d(smem + WA_OFF_REL, &tmap_rel, bar_qk, 0, 0);
-      mbar_arrive_expect_tx(bar_v, 28672);
-      tma_load_4d(smem + WA_OFF_V, &tmap_kv, bar_v, 2 * p.D + h * 64, wx * 14, wy * 14, b);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_qk, Cfg::SUB * (14336 + 28672 + 8192));
+      for (int s = 0; s < Cfg::SUB; ++s) {
+        tma_load_4d(smem + Cfg::OFF_Q + s * Cfg::Q_SUB, &tmap_q, bar_qk, h * HD + s * 64, wx * 14, wy * 14 + mt * 7, b);
+        tma_load_4d(smem + Cfg::OFF_K + s * Cfg::KV_SUB, &tmap_kv, bar_qk, p.D + h * HD + s * 64, wx * 14, wy * 14, b);
+        tma_load_2d(smem + Cfg::OFF_REL + s * 8192, &tmap_rel, bar_qk, s * 64, 0);
+      }
+      mbar_arrive_expect_tx(bar_v, Cfg::SUB * 28672);
+      for (int s = 0; s < Cfg::SUB; ++s)
+        tma_load_4d(smem + Cfg::OFF_V + s * Cfg::KV_SUB, &tmap_kv, bar_v, 2 * p.D + h * HD + s * 64, wx * 14, wy * 14, b);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 224, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
-      const uint32_t sq = smem_u32(smem + WA_OFF_Q), sk = smem_u32(smem + WA_OFF_K);
-      const uint32_t sv = smem_u32(smem + WA_OFF_V), sp = smem_u32(smem + WA_OFF_P);
-      const uint32_t sr = smem_u32(smem + WA_OFF_REL);
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
+    constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 224, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);  // A = P from TMEM, V MN-major
+    const bool leader = elect_one();
+    const uint32_t sq = smem_u32(smem + Cfg::OFF_Q), sk = smem_u32(smem + Cfg::OFF_K);
+    const uint32_t sv = smem_u32(smem + Cfg::OFF_V), sr = smem_u32(smem + Cfg::OFF_REL);
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    if (leader) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_bf16(tmem_base + WA_COL_T, make_sdesc_sw128(sq + ks * 32, 16, 1024), make_sdesc_sw128(sr + ks * 32, 16, 1024),
-                  idesc_t, ks != 0);
+      for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+        const uint32_t ko = (ks & 3) * 32;
+        umma_bf16(tmem_base + Cfg::COL_T, make_sdesc_sw128(sq + (ks >> 2) * Cfg::Q_SUB + ko, 16, 1024),
+                  make_sdesc_sw128(sr + (ks >> 2) * 8192 + ko, 16, 1024), idesc_t, ks != 0);
+      }
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_bf16(tmem_base + WA_COL_S, make_sdesc_sw128(sq + ks * 32, 16, 1024), make_sdesc_sw128(sk + ks * 32, 16, 1024),
-                  idesc_s, ks != 0);
+      for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+        const uint32_t ko = (ks & 3) * 32;
+        umma_bf16(tmem_base + Cfg::COL_S, make_sdesc_sw128(sq + (ks >> 2) * Cfg::Q_SUB + ko, 16, 1024),
+                  make_sdesc_sw128(sk + (ks >> 2) * Cfg::KV_SUB + ko, 16, 1024), idesc_s, ks != 0);
+      }
       umma_commit(s_full);
-      mbar_wait(bar_v, 0);
-      mbar_wait(p_full, 0);
-      tc_fence_after();
+    }
+    __syncwarp();
+    mbar_wait(bar_v, 0);
+    mbar_wait(p_full, 0);
+    tc_fence_after();
+    if (leader) {
 #pragma unroll
-      for (int ks = 0; ks < 14; ++ks)  // 224 keys, 16 per MMA
-        umma_bf16(tmem_base + WA_COL_O, make_sdesc_sw128(sp + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                  make_sdesc_sw128(sv + ks * 2048, 16384, 1024), idesc_o, ks != 0);
+      for (int ks = 0; ks < 14; ++ks)  // 224 keys, 16 per MMA; P: 8 TMEM columns per step
+        umma_bf16_ts(tmem_base + Cfg::COL_O, tmem_base + Cfg::COL_S + ks * 8,
+                     make_sdesc_sw128(sv + ks * 2048, Cfg::KV_SUB, 1024), idesc_o, ks != 0);
       umma_commit(o_full);
     }
+    __syncwarp();
   } else {
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
@@ -118,15 +143,14 @@ window_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int yy = r >> 4, x = r & 15;
     const int y = mt * 7 + yy;
     const float c1 = p.scale * WA_LOG2E;
-    float* sT = reinterpret_cast<float*>(smem + WA_OFF_T) + r * WA_T_LD;
-    uint8_t* sP = smem + WA_OFF_P;
+    float* sT = reinterpret_cast<float*>(smem + Cfg::OFF_T) + r * WA_T_LD;
 
     mbar_wait(s_full, 0);
     tc_fence_after();
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld32(lane_addr + WA_COL_T + c * 32, v);
+      tmem_ld32(lane_addr + Cfg::COL_T + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) sT[c * 32 + i] = __uint_as_float(v[i]) * WA_LOG2E;
@@ -144,7 +168,7 @@ window_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
     for (int c = 0; c < 7; ++c) {
       uint32_t v[32];
-      tmem_ld32(lane_addr + WA_COL_S + c * 32, v);
+      tmem_ld32(lane_addr + Cfg::COL_S + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i)
@@ -154,24 +178,21 @@ window_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
     for (int c = 0; c < 7; ++c) {
       uint32_t v[32];
-      tmem_ld32(lane_addr + WA_COL_S + c * 32, v);
+      tmem_ld32(lane_addr + Cfg::COL_S + c * 32, v);
       tmem_ld_wait();
-      float pr[32];
+      uint32_t pk[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        pr[i] = exp2f(fmaf(__uint_as_float(v[i]), c1, bw[i & 15]) + (bh[2 * c + (i >> 4)] - m_row));
-        l_row += pr[i];
+      for (int i = 0; i < 16; ++i) {
+        const float e0 = exp2f(fmaf(__uint_as_float(v[2 * i]), c1, bw[(2 * i) & 15]) + (bh[2 * c + ((2 * i) >> 4)] - m_row));
+        const float e1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), c1, bw[(2 * i + 1) & 15]) + (bh[2 * c + ((2 * i + 1) >> 4)] - m_row));
+        l_row += e0 + e1;
+        pk[i] = pack_bf16(e0, e1);
       }
-      uint8_t* sub = sP + (c >> 1) * 16384;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint4 pk = make_uint4(pack_bf16(pr[8 * g], pr[8 * g + 1]), pack_bf16(pr[8 * g + 2], pr[8 * g + 3]),
-                                    pack_bf16(pr[8 * g + 4], pr[8 * g + 5]), pack_bf16(pr[8 * g + 6], pr[8 * g + 7]));
-        *reinterpret_cast<uint4*>(sub + sw128_offset(r, (c & 1) * 4 + g)) = pk;
-      }
+      // P chunk c overwrites S columns [16c, 16c+16): already consumed (chunk c/2 <= c, chunk 0 is in registers)
+      tmem_st16(lane_addr + Cfg::COL_S + c * 16, pk);
     }
+    tmem_st_wait();
     tc_fence_before();
-    fence_proxy_async();
     __syncwarp();
     if (lane == 0) mbar_arrive(p_full);
 
@@ -180,16 +201,16 @@ window_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int gy = wy * 14 + y, gx = wx * 14 + x;
     const bool valid = (r < 112) && (x < 14) && (gy < 64) && (gx < 64);
     const float inv_l = 1.0f / l_row;
-    __nv_bfloat16* dst = p.out + ((size_t)(b * 64 + gy) * 64 + gx) * p.D + h * 64;
+    __nv_bfloat16* dst = p.out + ((size_t)(b * 64 + gy) * 64 + gx) * p.D + h * HD;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld32(lane_addr + WA_COL_O + c * 32, v);
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t v[16];
+      tmem_ld16(lane_addr + Cfg::COL_O + c * 16, v);
       tmem_ld_wait();
       if (valid) {
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 16);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]) * inv_l;
@@ -207,18 +228,28 @@ window_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   }
 }
 
-int window_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const WindowParams& p,
-                    cudaStream_t st) {
+template <int HD>
+static int launch_window(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const WindowParams& p,
+                         cudaStream_t st) {
+  using Cfg = WinCfg<HD>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM_BYTES) !=
+    if (cudaFuncSetAttribute(window_attn_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
         cudaSuccess)
       return WM_ERR_CUDA;
     attr_set = true;
   }
   dim3 grid(2, 25 * p.H, p.B);
-  window_attn_kernel<<<grid, WA_THREADS, WA_SMEM_BYTES, st>>>(tq, tkv, trel, p);
+  window_attn_kernel<HD><<<grid, WA_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tkv, trel, p);
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// tq: box (64, 16, 7, 1) over qkv [B,64,64,3D]; tkv: box (64, 16, 14, 1); trel: box (64, 64) over the [64, hd] table
+int window_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const WindowParams& p, int hd,
+                    cudaStream_t st) {
+  if (hd == 64) return launch_window<64>(tq, tkv, trel, p, st);
+  if (hd == 80) return launch_window<80>(tq, tkv, trel, p, st);
+  return WM_ERR_SHAPE;
 }
 
 }  // namespace wm

@@ -72,6 +72,7 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, __nv
   switch (D) {
     WM_LN_CASE(1)
     WM_LN_CASE(2)
+    WM_LN_CASE(5)
     WM_LN_CASE(6)
     WM_LN_CASE(8)
     WM_LN_CASE(10)

@@ -60,7 +60,7 @@ struct WindowParams {
   int D;        // embedding dim (q at col h*64, k at D + h*64, v at 2D + h*64 in the [B,64,64,3D] qkv tensor)
   __nv_bfloat16* out;  // [B,64,64,D]
 };
-int window_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const WindowParams& p,
+int window_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const WindowParams& p, int hd,
                     cudaStream_t st);
 int window2_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const CUtensorMap& tout,
                      const WindowParams& p, int num_sms, cudaStream_t st);

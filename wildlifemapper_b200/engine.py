@@ -76,11 +76,11 @@ class EncoderEngine:
     """Derived weights + schedule for fft + ImageEncoderViT on one device."""
 
     def __init__(self, embed_dim: int, depth: int, num_heads: int, global_attn_indexes, device):
-        if embed_dim // num_heads != 64:
+        if embed_dim % num_heads != 0 or embed_dim // num_heads not in (64, 80):
             raise NotImplementedError(
-                f"head_dim {embed_dim // num_heads} is not supported yet by the tcgen05 attention kernels (need 64); "
-                "ViT-H (head_dim 80) is listed as remaining work in DESIGN.md")
+                f"head_dim {embed_dim / num_heads} is not supported by the tcgen05 attention kernels (64: ViT-B/L, 80: ViT-H)")
         self.D, self.depth, self.H = embed_dim, depth, num_heads
+        self.hd = embed_dim // num_heads
         self.glob = tuple(global_attn_indexes)
         self.device = torch.device(device)
         self.ws = _Workspace(self.device)
@@ -131,10 +131,10 @@ class EncoderEngine:
             w[p + "proj_b"] = _f32(g(b + "attn.proj.bias").float() + pw @ b_v)
             rh, rw = g(b + "attn.rel_pos_h"), g(b + "attn.rel_pos_w")
             if i in self.glob:
-                t = torch.zeros(256, 64, device=dev, dtype=torch.bfloat16)
+                t = torch.zeros(256, self.hd, device=dev, dtype=torch.bfloat16)
                 t[:127], t[128:255] = rh.to(torch.bfloat16), rw.to(torch.bfloat16)
             else:
-                t = torch.zeros(64, 64, device=dev, dtype=torch.bfloat16)
+                t = torch.zeros(64, self.hd, device=dev, dtype=torch.bfloat16)
                 t[:27], t[32:59] = rh.to(torch.bfloat16), rw.to(torch.bfloat16)
             w[p + "rel"] = t
             for n in ("norm1", "norm2"):
@@ -213,13 +213,13 @@ class EncoderEngine:
         qkv = ws.get("qkv", (M, 3 * D), bf)
         att = ws.get("att", (M, D), bf)
         hid = ws.get("hid", (M, 4 * D), bf)
-        scale = 64 ** -0.5
+        scale = self.hd ** -0.5
         for i in range(self.depth):
             p = f"b{i}."
             ops.layernorm(x, w[p + "norm1_g"], w[p + "norm1_b"], xn, None, None, 0, None, 1e-6)
             _gemm(xn, w[p + "qkv_w"], w[p + "qkv_b"], out_bf16=qkv)
             if i in self.glob:
-                ops.attn_flash(qkv, 0, qkv, D, qkv, 2 * D, w[p + "rel"], att, B, H, NTOK, NTOK, 64, scale)
+                ops.attn_flash(qkv, 0, qkv, D, qkv, 2 * D, w[p + "rel"], att, B, H, NTOK, NTOK, self.hd, scale)
             else:
                 ops.attn_window(qkv, w[p + "rel"], att, H, scale)
             _gemm(att, w[p + "proj_w"], w[p + "proj_b"], x, M, out_f32=x)

@@ -146,7 +146,7 @@ def _attn_flash(q, q_col0, k, k_col0, v, v_col0, rel_table, out, B, H, Tq, Tk, h
         _chk(t, torch.bfloat16, "attn_flash." + n)
         assert t.dim() == 2
     _chk(rel_table, torch.bfloat16, "attn_flash.rel_table")
-    assert rel_table is None or (rel_table.is_contiguous() and tuple(rel_table.shape) == (256, 64))
+    assert rel_table is None or (rel_table.is_contiguous() and tuple(rel_table.shape) == (256, hd))
     assert out.shape[0] >= B * Tq and out.shape[1] >= H * hd
     _lib.call("wm_attn_flash", q.data_ptr(), q.shape[0], q.shape[1], q.stride(0), int(q_col0),
               k.data_ptr(), k.shape[0], k.shape[1], k.stride(0), int(k_col0),
@@ -164,7 +164,7 @@ def _attn_window(qkv, rel_table, out, H, scale):
     assert qkv.is_contiguous() and out.is_contiguous() and rel_table.is_contiguous()
     D = out.shape[-1]
     B = out.numel() // (4096 * D)
-    assert qkv.numel() == B * 4096 * 3 * D and tuple(rel_table.shape) == (64, 64)
+    assert qkv.numel() == B * 4096 * 3 * D and tuple(rel_table.shape) == (64, D // H)
     _lib.call("wm_attn_window", qkv.data_ptr(), rel_table.data_ptr(), out.data_ptr(), B, H, D, float(scale), _stream())
 
 

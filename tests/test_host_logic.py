@@ -109,8 +109,13 @@ def test_engine_prepare_layouts_on_cpu():
     # conv3x3 weight layout: k = (dy*3+dx)*C + c
     wt = sd["neck.2.weight"]
     assert torch.equal(w["neck2_w"][5, (1 * 3 + 2) * 256 + 7].float(), wt[5, 7, 1, 2].to(torch.bfloat16).float())
+    # ViT-H (head dim 80) is supported: its rel-pos tables are [*, 80]; any other head dim is a loud error
+    sd80 = {k[len("image_encoder."):]: v for k, v in make_state_dict("vit_t80", seed=0).items() if k.startswith("image_encoder.")}
+    eng80 = EncoderEngine(640, 2, 8, (1,), device="cpu")
+    eng80.prepare(sd80)
+    assert eng80.w["b0.rel"].shape == (64, 80) and eng80.w["b1.rel"].shape == (256, 80)
     with pytest.raises(NotImplementedError):
-        EncoderEngine(1280, 32, 16, (7, 15, 23, 31), device="cpu")  # ViT-H head_dim 80: stated gap, loud error
+        EncoderEngine(768, 12, 8, (2,), device="cpu")  # head dim 96
 
 
 def test_shard_bounds_cover_everything():

@@ -66,6 +66,53 @@ __global__ void __launch_bounds__(256, 1) bench(float* out, long long* cycles, i
         acc[i & 3] += e0 + e1;
         pk ^= pack(e0, e1);
       }
+    } else if (VARIANT >= 6 && VARIANT <= 9) {
+      // the flash-v4 rel-pos chunk: y = v*c1 + tw (FFMA2), [max (FMNMX)], y + d (FADD2), 2 x MUFU, pack, row sum (FADD2)
+      //   6: as in the kernel   7: without the FMNMX   8: scalar FFMA / FADD instead of the packed forms   9: 7 + order-pinned
+      float tw[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) tw[i] = 0.001f * (float)((i * 37 + threadIdx.x) & 63);
+      float ymax0 = -1e30f, ymax1 = -1e30f;
+      unsigned long long cs0 = 0ull, cs1 = 0ull;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int k = c * 32 + 2 * i;
+          float y0, y1, a0, a1;
+          if (VARIANT == 8) {
+            y0 = fmaf(y[k], 0.18f, tw[k & 63]); y1 = fmaf(y[k + 1], 0.18f, tw[(k + 1) & 63]);
+            a0 = y0 + d; a1 = y1 + d;
+          } else {
+            unsigned long long vp, twp, c1p, dp, y2, yd;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(vp) : "f"(y[k]), "f"(y[k + 1]));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(twp) : "f"(tw[k & 63]), "f"(tw[(k + 1) & 63]));
+            asm("mov.b64 %0, {%1, %1};" : "=l"(c1p) : "f"(0.18f));
+            asm("mov.b64 %0, {%1, %1};" : "=l"(dp) : "f"(d));
+            asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(y2) : "l"(vp), "l"(c1p), "l"(twp));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(y2));
+            asm("add.rn.f32x2 %0, %1, %2;" : "=l"(yd) : "l"(y2), "l"(dp));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(yd));
+          }
+          if (VARIANT == 6 || VARIANT == 8) { ymax0 = fmaxf(ymax0, y0); ymax1 = fmaxf(ymax1, y1); }
+          float e0, e1;
+          if (VARIANT == 9) {
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+          } else {
+            e0 = ex2(a0); e1 = ex2(a1);
+          }
+          unsigned long long ep;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(ep) : "f"(e0), "f"(e1));
+          if (i & 1) asm("add.rn.f32x2 %0, %0, %1;" : "+l"(cs1) : "l"(ep));
+          else asm("add.rn.f32x2 %0, %0, %1;" : "+l"(cs0) : "l"(ep));
+          pk ^= pack(e0, e1);
+        }
+      }
+      float s0, s1, s2, s3;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(cs0));
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(s2), "=f"(s3) : "l"(cs1));
+      acc[0] += s0 + s1 + s2 + s3 + ymax0 * 1e-30f + ymax1 * 1e-30f;
     } else if (VARIANT == 5) {
 #pragma unroll
       for (int i = 0; i < 128; ++i) {
@@ -104,6 +151,10 @@ int main() {
     run<3>("polynomial exp2 (FMA pipe)", w);
     run<4>("mix, 25% polynomial", w);
     run<5>("max phase (FFMA + FMNMX)", w);
+    run<6>("v4 rel-pos chunk (packed, FMNMX)", w);
+    run<7>("v4 rel-pos chunk without FMNMX", w);
+    run<8>("v4 rel-pos chunk, scalar FFMA/FADD", w);
+    run<9>("v4 rel-pos chunk, no FMNMX, pinned", w);
   }
   return 0;
 }

@@ -170,8 +170,8 @@ def test_attn_small(Tq, Tk, hd, H):
 
 @pytest.mark.parametrize("hd,H,T", [(64, 2, 256), (64, 3, 4096), (128, 2, 512), (128, 8, 4096), (80, 3, 1024)])
 def test_attn_flash_plain(hd, H, T, flash_version):
-    if hd == 80 and flash_version != 3:
-        pytest.skip("head dim 80 (ViT-H) is served by the v3 kernel only")
+    if hd == 80 and flash_version < 3:
+        pytest.skip("head dim 80 (ViT-H) is served by the v3 / v4 kernels only")
     B = 2 if T <= 512 else 1
     q = rnd(B * T, H * hd, seed=24)
     kv = rnd(B * T, 2 * H * hd, seed=25)
@@ -203,13 +203,13 @@ def test_attn_flash_rising_maxima(hd, flash_version):
     assert (out.float() - ref).abs().max().item() < 3e-2
 
 
-@pytest.fixture(params=[3, 2, 1])
+@pytest.fixture(params=[4, 3, 2, 1])
 def flash_version(request):
-    """All flash-attention kernel generations stay parity-checked (3 = default)."""
+    """All flash-attention kernel generations stay parity-checked (4 = default)."""
     from wildlifemapper_b200 import lib
     lib.call("wm_set_flash_version", request.param)
     yield request.param
-    lib.call("wm_set_flash_version", 3)
+    lib.call("wm_set_flash_version", 4)
 
 
 def relpos_bias(q, rel_h, rel_w, S):
@@ -225,8 +225,8 @@ def relpos_bias(q, rel_h, rel_w, S):
 
 @pytest.mark.parametrize("hd", [64, 80])
 def test_attn_flash_global_relpos(flash_version, hd):
-    if hd == 80 and flash_version != 3:
-        pytest.skip("head dim 80 (ViT-H) is served by the v3 kernel only")
+    if hd == 80 and flash_version < 3:
+        pytest.skip("head dim 80 (ViT-H) is served by the v3 / v4 kernels only")
     B, H, T = 2, 3, 4096
     D = H * hd
     qkv = rnd(B * T, 3 * D, seed=26)

@@ -1,23 +1,16 @@
-// Flash attention v3 on tcgen05 / TMEM (sm_100a): global 64x64 attention with decomposed rel-pos bias and the
-// HFC cross-attention.  Same math and reference sites as attn_flash.cu (image_encoder.py:246-262, 347-383,
-// 500-503).  Restructured around what the v2 profiles showed (profiles/r01b_*, r01c_*): with 64-key tiles and
-// P staged in shared memory, the 128 x 64 x 16 MMAs re-read their A operand from shared memory every step and
-// the kernel ran out of shared-memory bandwidth (operand reads + P stores + TMA fills ~1.4-1.8k cycles per key
-// tile against ~1.0k cycles of MUFU work), and the softmax warps spent ~45 % of their time waiting for S.
+// Flash attention v4 on tcgen05 / TMEM (sm_100a): global 64x64 attention with decomposed rel-pos bias and the HFC
+// cross-attention.  Same math and reference sites as attn_flash.cu (image_encoder.py:246-262, 347-383, 500-503) and the
+// same building blocks as v3 (attn_flash3.cu): two 128-query tiles per CTA, P kept in tensor memory (tcgen05.mma "ts"
+// form), O accumulated in TMEM with lazy rescaling, bias_w in registers and T_h resident in TMEM, setmaxnreg split,
+// warp-uniform TMA / MMA issue.  What changed, from the v3 event traces (profiles/r01g_flash3_trace_*.txt): in v3 the
+// next score tile S_t(j+1) aliases P_t(j) and can only be issued after P_t(j) V, so every softmax warpgroup sat idle
+// for ~1500 of every ~4500 cycles waiting for its next scores, and the MUFU ran at ~45 %.  Here
 //
-//   * one CTA = TWO 128-query tiles of one (image, head); key tiles of 128 (two key rows of the 64x64 grid);
-//   * P never touches shared memory: each softmax thread holds its whole 128-score row in registers, and writes
-//     the bf16 probabilities back into the first 64 TMEM columns of its own S tile (tcgen05.st); the P V MMA
-//     reads its A operand from TENSOR MEMORY (tcgen05.mma "ts" form) -- shared memory carries only Q, K, V;
-//   * the two query tiles ping-pong: while the 4 softmax warps of one tile run exp2 on the MUFU, the tensor core
-//     runs P V and the next S of the other tile;
-//   * O accumulates in TMEM across key tiles with LAZY rescaling (reference maximum only raised -- and O, l
-//     rescaled through tcgen05.ld / tcgen05.st -- when a tile exceeds it by more than 2^8); row sums in fp32
-//     registers;
-//   * rel-pos: T_w = Q Rw^T and T_h = Q Rh_slice^T are computed once per CTA by the tensor core; bias_w[64] lives
-//     in registers, T_h stays resident in the spare TMEM columns (one 32-bit read per key row and tile);
-//   * register budget: setmaxnreg moves registers from the producer / MMA warpgroup (40) to the softmax
-//     warpgroups (232).
+//   * the softmax works in steps of 64 keys (ONE key row of the 64x64 grid: bias_h is a single scalar per step) and
+//     each query tile owns TWO 64-column score buffers: the MMA warp runs two steps ahead (P_t(j) V, then S_t(j+2)
+//     into the buffer step j just released), so in steady state the scores of the next step are already waiting
+//     when a warpgroup finishes a step, and the MUFU always has two warps per scheduler to choose from;
+//   * K and V still arrive as 128-key TMA tiles; the two halves of a stage are addressed by descriptor offset.
 //
 //   warp 0       TMA producer (Q tiles, tables, K and V rings)
 //   warp 1       tcgen05.mma issuer          warp 2  TMEM allocator
@@ -27,26 +20,23 @@
 
 namespace wm {
 
-constexpr int F3_THREADS = 384;
-constexpr float F3_LOG2E = 1.4426950408889634f;
-constexpr float F3_TAU = 8.0f;  // lazy-rescale threshold (log2 units): p <= 2^8 between rescales
-
 #ifdef WM_F3_TRACE
-// Diagnostics build only: per-event SM clock stamps of CTA (0,0,0) -- [role][key tile][event]; role 0/1 = softmax
-// warpgroup of query tile 0/1 (0 S ready, 1 scores loaded, 2 maximum known, 3 turn acquired, 4 all P stores issued,
-// 5 P stores complete), role 2 = MMA issuer (0 P_0 seen, 1 P_0 V issued, 2 S_0 issued, 3 P_1 seen, 4 P_1 V issued,
-// 5 S_1 issued).
-__device__ unsigned long long g_f3_trace[3][64][8];  // (also used by attn_flash4.cu)
-#define F3_TRACE(role, j, ev)                                                                   \
+// diagnostics build: SM-clock event trace of CTA (0,0,0) ([role][step][event]; see profiles/flash4_trace.py)
+__device__ unsigned long long g_f4_trace[3][64][8];
+#define F4_TRACE(role, j, ev)                                                                   \
   do {                                                                                          \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64) g_f3_trace[role][j][ev] = clock64(); \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64) g_f4_trace[role][j][ev] = clock64(); \
   } while (0)
 #else
-#define F3_TRACE(role, j, ev) do { } while (0)
+#define F4_TRACE(role, j, ev) do { } while (0)
 #endif
 
+constexpr int F4_THREADS = 384;
+constexpr float F4_LOG2E = 1.4426950408889634f;
+constexpr float F4_TAU = 8.0f;  // lazy-rescale threshold (log2 units): p <= 2^8 between rescales
+
 template <int HD, bool RELPOS>
-struct Flash3Cfg {
+struct Flash4Cfg {
   static_assert(HD % 16 == 0 && HD >= 64 && HD <= 128, "head dim");
   static_assert(!RELPOS || HD <= 96, "rel-pos variant: tensor-memory budget");
   static constexpr int SUB = (HD + 63) / 64;       // 64-column (128-byte) sub-tiles per operand row (a partial second
@@ -67,7 +57,7 @@ struct Flash3Cfg {
   static constexpr int OFF_BAR = OFF_V + STAGES * TILE_BYTES + (TAB_ALIAS ? 0 : TAB_BYTES);
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  // TMEM columns: S_t at 128 t (P_t = bf16 pairs in its first 64 columns), O_t at 256 + HD t, then the resident T_h:
+  // TMEM columns: S_t buffer b at 128 t + 64 b (P = bf16 pairs in its first 32 columns), O_t at 256 + HD t, then T_h:
   //   head dim 64: fp32, 64 columns per tile (+ column 64 in a register);  larger: fp16 pairs, 33 of 40 columns per tile
   static constexpr int COL_O = 256;
   static constexpr int COL_TH = COL_O + 2 * HD;
@@ -77,12 +67,12 @@ struct Flash3Cfg {
   static_assert(COL_TH + (RELPOS ? 2 * TH_STRIDE : 0) <= 512, "TMEM budget");
 };
 
-template <int HD, bool RELPOS, bool TURNS>
-__global__ void __launch_bounds__(F3_THREADS, 1)
-flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+template <int HD, bool RELPOS>
+__global__ void __launch_bounds__(F4_THREADS, 1)
+flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
               const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_rel,
               const FlashParams p) {
-  using Cfg = Flash3Cfg<HD, RELPOS>;
+  using Cfg = Flash4Cfg<HD, RELPOS>;
   constexpr int NS = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -92,16 +82,18 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint64_t* k_empty = bars + 5;   // [4]
   uint64_t* v_full = bars + 9;    // [4]
   uint64_t* v_empty = bars + 13;  // [4]
-  uint64_t* s_full = bars + 17;   // [2]  S_t(j) complete (implies P_t(j-1) V has completed: in-order tensor pipe)
-  uint64_t* p_full = bars + 19;   // [2]  P_t(j) stored to TMEM by the 4 warps of tile t
-  uint64_t* o_full = bars + 21;   // [2]
-  uint64_t* t_full = bars + 23;   // rel-pos table products complete
-  uint64_t* t_done = bars + 24;   // ... and drained out of the S / O columns by the 8 softmax warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  uint64_t* s_full = bars + 17;   // [2 tiles][2 buffers]  S_t(j) complete
+  uint64_t* p_full = bars + 21;   // [2 tiles][2 buffers]  P_t(j) stored to TMEM by the 4 warps of tile t
+  uint64_t* pv_done = bars + 25;  // [2]  P_t(j) V complete (only waited on by the rare rescale path)
+  uint64_t* o_full = bars + 27;   // [2]
+  uint64_t* t_full = bars + 29;   // rel-pos table products complete
+  uint64_t* t_done = bars + 30;   // ... and drained out of the S / O columns by the 8 softmax warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
 
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
-  const int nk = p.Tk / 128;
+  const int nk = p.Tk / 128;  // 128-key TMA tiles
+  const int ns = p.Tk / 64;   // 64-key softmax / MMA steps
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -114,9 +106,12 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&pv_done[i], 1);
       mbar_init(&o_full[i], 1);
     }
     mbar_init(t_full, 1);
@@ -182,7 +177,7 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       }
     } else if (warp == 1) {
       // ------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);  // A = P from TMEM (K-major), V is MN-major
       const bool leader = elect_one();  // the same lane issues every tcgen05.mma / tcgen05.commit
       const uint32_t sq = smem_u32(smem + Cfg::OFF_Q);
@@ -218,66 +213,70 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         mbar_wait(t_done, 0);  // both warpgroups have drained the scratch out of the S / O columns
         tc_fence_after();
       }
-      auto issue_s = [&](int t, int st) {  // S_t = Q_t K^T into TMEM columns [128 t, 128 t + 128)
+      // S_t(step) = Q_t K(step)^T (128 x 64 x HD) into score buffer (step & 1) of tile t; K rows of step: half (step & 1)
+      // of stage (step / 2) % NS.  (MMAs that accumulate into the same tensor-memory tile are serialised by the
+      // accumulator round trip, ~90 cycles per 128 x 64 x 16 step; issuing the two tiles' chains interleaved shortens
+      // the issue time but forces the tiles into lockstep and measured slower end to end: profiles/r01u_flash4_*.txt.)
+      auto issue_s = [&](int t, int step) {
         if (leader) {
+          const int kst = (step >> 1) % NS;
           const uint64_t qd = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES, 16, 1024);
-          const uint64_t kd = make_sdesc_sw128(smem_u32(smem + Cfg::OFF_K + st * Cfg::TILE_BYTES), 16, 1024);
+          const uint64_t kd = make_sdesc_sw128(smem_u32(smem + Cfg::OFF_K + kst * Cfg::TILE_BYTES) + (step & 1) * 8192, 16, 1024);
 #pragma unroll
           for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
             const uint32_t off = (uint32_t)((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);  // address field is bytes >> 4
-            umma_bf16(tmem_base + t * 128, qd + off, kd + off, idesc_s, ks != 0);
+            umma_bf16(tmem_base + t * 128 + (step & 1) * 64, qd + off, kd + off, idesc_s, ks != 0);
           }
-          umma_commit(&s_full[t]);
+          umma_commit(&s_full[t * 2 + (step & 1)]);
         }
         __syncwarp();
       };
+      // two steps ahead of the softmax (both from K tile 0)
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_s(0, 0);
       issue_s(1, 0);
+      issue_s(0, 1);
+      issue_s(1, 1);
       if (leader) umma_commit(&k_empty[0]);
       __syncwarp();
-      int st = 0;         // V stage of tile j
-      uint32_t ph = 0;
-      for (int j = 0; j < nk; ++j) {
-        const bool more = j + 1 < nk;
-        int kst = st + 1;  // K stage of tile j + 1
-        uint32_t kph = ph;
-        if (kst == NS) { kst = 0; kph ^= 1; }
-        const uint32_t sv = smem_u32(smem + Cfg::OFF_V + st * Cfg::TILE_BYTES);
+      for (int j = 0; j < ns; ++j) {
+        const int vst = (j >> 1) % NS;
+        const uint32_t vph = (uint32_t)((j >> 1) / NS) & 1u;
+        const bool more = j + 2 < ns;
+        const uint32_t sv = smem_u32(smem + Cfg::OFF_V + vst * Cfg::TILE_BYTES) + (j & 1) * 8192;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], j & 1);
-          if (t == 0) mbar_wait(&v_full[st], ph);
+          if (leader) F4_TRACE(2, j, 4 * t);
+          mbar_wait(&p_full[t * 2 + (j & 1)], (uint32_t)(j >> 1) & 1u);
+          if (leader) F4_TRACE(2, j, 4 * t + 1);
+          if (t == 0) {
+            if ((j & 1) == 0) mbar_wait(&v_full[vst], vph);
+            if (more && (j & 1) == 0) {  // step j + 2 opens K tile (j + 2) / 2
+              const int kt = (j + 2) >> 1;
+              mbar_wait(&k_full[kt % NS], (uint32_t)(kt / NS) & 1u);
+            }
+          }
           tc_fence_after();
-          if (leader) F3_TRACE(2, j, 3 * t);
           if (leader) {
             const uint64_t vd = make_sdesc_sw128(sv, 16384, 1024);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)  // 128 keys, 16 per MMA; P_t: 8 TMEM columns per step; V: 2048 B per step
-              umma_bf16_ts(tmem_base + Cfg::COL_O + t * HD, tmem_base + t * 128 + ks * 8,
+            for (int ks = 0; ks < 4; ++ks)  // 64 keys, 16 per MMA; P: 8 TMEM columns per step; V: 2048 B per step
+              umma_bf16_ts(tmem_base + Cfg::COL_O + t * HD, tmem_base + t * 128 + (j & 1) * 64 + ks * 8,
                            vd + (uint32_t)(ks * (2048 >> 4)), idesc_pv, (j | ks) != 0);
+            umma_commit(&pv_done[t]);
+            if (j == ns - 1) umma_commit(&o_full[t]);
           }
-          if (leader) F3_TRACE(2, j, 3 * t + 1);
           __syncwarp();
-          if (more) {
-            if (t == 0) {
-              mbar_wait(&k_full[kst], kph);
-              tc_fence_after();
-            }
-            issue_s(t, kst);  // overwrites S_t / P_t: ordered behind the P V MMAs above
-            if (leader) F3_TRACE(2, j, 3 * t + 2);
-          } else {
-            if (leader) umma_commit(&o_full[t]);
-            __syncwarp();
-          }
+          if (leader) F4_TRACE(2, j, 4 * t + 2);
+          if (more) issue_s(t, j + 2);  // reuses the score buffer step j just released (behind its P V in the pipe)
+          if (leader) F4_TRACE(2, j, 4 * t + 3);
         }
         if (leader) {
-          umma_commit(&v_empty[st]);
-          if (more) umma_commit(&k_empty[kst]);
+          if (j & 1) umma_commit(&v_empty[vst]);                       // both halves of the V tile consumed
+          if (more && (j & 1)) umma_commit(&k_empty[((j + 2) >> 1) % NS]);  // both halves of K tile (j + 2) / 2 issued
         }
         __syncwarp();
-        if (++st == NS) { st = 0; ph ^= 1; }
       }
     }
   } else {
@@ -289,7 +288,7 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const uint32_t s_addr = lane_addr + t * 128;
     const uint32_t o_addr = lane_addr + Cfg::COL_O + t * HD;
-    const float c1 = p.scale * F3_LOG2E;
+    const float c1 = p.scale * F4_LOG2E;
     float tw[RELPOS ? 64 : 1];
     float bh64 = 0.0f;                                            // T_h column 64 (only needed by key row 0)
     const int hi = r >> 6;                                        // image row of this query inside the tile (warp-uniform)
@@ -309,16 +308,16 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         uint32_t pkh[32];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          pkh[i] = pack_f16(__uint_as_float(a[2 * i]) * F3_LOG2E, __uint_as_float(a[2 * i + 1]) * F3_LOG2E);
-          pkh[16 + i] = pack_f16(__uint_as_float(bq[2 * i]) * F3_LOG2E, __uint_as_float(bq[2 * i + 1]) * F3_LOG2E);
+          pkh[i] = pack_f16(__uint_as_float(a[2 * i]) * F4_LOG2E, __uint_as_float(a[2 * i + 1]) * F4_LOG2E);
+          pkh[16 + i] = pack_f16(__uint_as_float(bq[2 * i]) * F4_LOG2E, __uint_as_float(bq[2 * i + 1]) * F4_LOG2E);
         }
         tmem_st32(th_addr, pkh);
-        tmem_st1(th_addr + 32, pack_f16(__uint_as_float(cq[0]) * F3_LOG2E, 0.0f));
+        tmem_st1(th_addr + 32, pack_f16(__uint_as_float(cq[0]) * F4_LOG2E, 0.0f));
         tmem_st_wait();
       } else {
         const uint32_t x = tmem_ld1(lane_addr + Cfg::COL_O + t * 16);
         tmem_ld_wait();
-        bh64 = __uint_as_float(x) * F3_LOG2E;
+        bh64 = __uint_as_float(x) * F4_LOG2E;
       }
       // bias_w[kw] = T_w[qj + 63 - kw]: per-thread scatter through a private XOR-swizzled 32-float smem row
       float* scr = reinterpret_cast<float*>(smem + Cfg::OFF_TAB) + ((t * 128 + r) << 5);
@@ -332,7 +331,7 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int kw = qj + 63 - (c * 32 + i) - half * 32;
-            if (kw >= 0 && kw < 32) scr[((((kw >> 2) ^ (r & 7)) << 2) | (kw & 3))] = __uint_as_float(v[i]) * F3_LOG2E;
+            if (kw >= 0 && kw < 32) scr[((((kw >> 2) ^ (r & 7)) << 2) | (kw & 3))] = __uint_as_float(v[i]) * F4_LOG2E;
           }
         }
 #pragma unroll
@@ -347,49 +346,39 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       if (lane == 0) mbar_arrive(t_done);
     }
 
-    // TURNS: the two warpgroups take turns on the MUFU (named barriers 2 + t) -- tile 0's exp2 phase runs while the
-    // tensor core works on tile 1 and vice versa, instead of both tiles stretching each other's exp2 phase.
-    if (TURNS && t == 1) named_bar_arrive(2, 256);  // tile 0 goes first
     float m_ref = -INFINITY, l_run = 0.0f;
-    for (int j = 0; j < nk; ++j) {
-      mbar_wait(&s_full[t], j & 1);
+    for (int j = 0; j < ns; ++j) {  // one step = 64 keys = key row j of the 64x64 grid
+      const uint32_t sj = s_addr + (j & 1) * 64;  // this step's score buffer; P = bf16 pairs over its first 32 columns
+      if (q4 == 0 && lane == 0) F4_TRACE(t, j, 0);
+      mbar_wait(&s_full[t * 2 + (j & 1)], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
-      if (q4 == 0 && lane == 0) F3_TRACE(t, j, 0);
-      // One pass over the 128 scores of this row in four 32-column chunks; the TMEM load of chunk c+1 is in flight
-      // while chunk c is processed.  Each chunk is first evaluated OPTIMISTICALLY against the current reference
-      // maximum; only if some row of the warp exceeds it by more than 2^TAU is the reference raised (O, l and the
-      // chunks of P already written are rescaled) and the chunk recomputed from the registers that still hold it.
-      // P chunk c (16 columns of bf16 pairs) overwrites S columns [16c, 16c+16), which chunk c/2 has already consumed.
+      if (q4 == 0 && lane == 0) F4_TRACE(t, j, 1);
+      // One pass over the 64 scores of this row in two 32-column chunks; the TMEM load of chunk 1 is in flight while
+      // chunk 0 is processed.  Each chunk is first evaluated OPTIMISTICALLY against the current reference maximum;
+      // only if some row of the warp exceeds it by more than 2^TAU is the reference raised (O, l and the chunk of P
+      // already written are rescaled) and the chunk recomputed from the registers that still hold it.
       uint32_t v[2][32];
-      tmem_ld32(s_addr, v[0]);
-      float bh0 = 0.0f, bh1 = 0.0f;
+      tmem_ld32(sj, v[0]);
+      tmem_ld32(sj + 32, v[1]);
+      float bh = 0.0f;
       if (RELPOS) {
-        const int c0 = hi + 63 - 2 * j;  // T_h index of key row 2j; key row 2j+1 is index c0 - 1 (>= 0)
+        const int c0 = hi + 63 - j;  // T_h index of key row j
         if (Cfg::TH_PACKED) {
           const uint32_t a0 = tmem_ld1(th_addr + (c0 >> 1));
-          const uint32_t a1 = tmem_ld1(th_addr + ((c0 - 1) >> 1));
           tmem_ld_wait();
-          bh0 = unpack_f16(a0, c0 & 1);
-          bh1 = unpack_f16(a1, (c0 - 1) & 1);
+          bh = unpack_f16(a0, c0 & 1);
         } else {
           const uint32_t a0 = tmem_ld1(th_addr + (c0 > 63 ? 63 : c0));
-          const uint32_t a1 = tmem_ld1(th_addr + c0 - 1);
           tmem_ld_wait();
-          bh0 = (c0 > 63) ? bh64 : __uint_as_float(a0) * F3_LOG2E;
-          bh1 = __uint_as_float(a1) * F3_LOG2E;
+          bh = (c0 > 63) ? bh64 : __uint_as_float(a0) * F4_LOG2E;
         }
       } else {
         tmem_ld_wait();
       }
-      if (q4 == 0 && lane == 0) F3_TRACE(t, j, 1);
-      if (TURNS) named_bar_sync(2 + t, 256);  // my turn on the MUFU
-      if (q4 == 0 && lane == 0) F3_TRACE(t, j, 3);
-      uint64_t ls2[2] = {0ull, 0ull};  // this tile's row sum (relative to m_ref): 2 packed pairs = 4 independent chains
+      uint64_t ls2[2] = {0ull, 0ull};  // this step's row sum (relative to m_ref): 2 packed pairs = 4 independent chains
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t(&cur)[32] = v[c & 1];
-        if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, v[(c + 1) & 1]);
-        const float bh = (c < 2) ? bh0 : bh1;
+      for (int c = 0; c < 2; ++c) {
+        uint32_t(&cur)[32] = v[c];
         float d = RELPOS ? bh - m_ref : -m_ref;  // +inf while m_ref = -inf: the first chunk always takes the exact path
         float ymax[2] = {-INFINITY, -INFINITY};
         uint64_t cs2[2] = {0ull, 0ull};  // 2 x 2 partial row sums (packed fp32x2: FFMA2 / FADD2 halve the FMA-pipe issue load)
@@ -397,37 +386,42 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const uint64_t c1p = pk2(c1, c1);
         {
           const uint64_t dp = pk2(d, d);
+          uint64_t yp[16];  // exp2 arguments (FFMA2 / FADD2: placed by the compiler where their exp2 needs them)
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const uint64_t vp = pk2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1]));
-            uint64_t yp;
             if (RELPOS) {
-              const uint64_t y2 = fma2(vp, c1p, pk2(tw[RELPOS ? (c & 1) * 32 + 2 * i : 0], tw[RELPOS ? (c & 1) * 32 + 2 * i + 1 : 0]));
+              const uint64_t y2 = fma2(vp, c1p, pk2(tw[RELPOS ? c * 32 + 2 * i : 0], tw[RELPOS ? c * 32 + 2 * i + 1 : 0]));
               float y0, y1;
               unpk2(y2, y0, y1);
               ymax[0] = fmaxf(ymax[0], y0);
               ymax[1] = fmaxf(ymax[1], y1);
-              yp = add2(y2, dp);
+              yp[i] = add2(y2, dp);
             } else {
               ymax[0] = fmaxf(ymax[0], __uint_as_float(cur[2 * i]));  // raw scores: c1 > 0
               ymax[1] = fmaxf(ymax[1], __uint_as_float(cur[2 * i + 1]));
-              yp = fma2(vp, c1p, dp);
+              yp[i] = fma2(vp, c1p, dp);
             }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
             float a0, a1;
-            unpk2(yp, a0, a1);
+            unpk2(yp[i], a0, a1);
             const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
             cs2[i & 1] = add2(cs2[i & 1], pk2(e0, e1));
             pk[i] = pack_bf16(e0, e1);
           }
         }
         const float m_chunk = RELPOS ? fmaxf(ymax[0], ymax[1]) + bh : fmaxf(ymax[0], ymax[1]) * c1;
-        const bool need = m_chunk > m_ref + F3_TAU;
+        const bool need = m_chunk > m_ref + F4_TAU;
         if (__any_sync(0xffffffffu, need)) {
-          // ---- exact path (rare after the first chunk of a row): raise the reference maximum.  s_full(j) implies that
-          // P(j-1) V has completed, so O is stable; the MMA thread does not touch this tile before p_full(j).
+          // ---- exact path (rare after the first chunk of a row): raise the reference maximum.  O must be stable: the
+          // MMA warp runs ahead with SCORE tiles only; P_t(j-1) V is the last MMA that touches O_t before p_full(j).
           const float m_new = need ? m_chunk : m_ref;
           const float alpha = ex2_approx(m_ref - m_new);  // 1 for lanes that did not need it, 0 on the very first chunk
           if (j > 0) {
+            mbar_wait(&pv_done[t], (uint32_t)(j - 1) & 1u);
+            tc_fence_after();
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k) {
               uint32_t o[16];
@@ -439,20 +433,17 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             }
           }
           l_run *= alpha;
-          if (c > 0) {  // P chunks of this tile written against the old reference
+          if (c > 0) {  // P chunk 0 of this step was written against the old reference
             tmem_st_wait();
+            uint32_t o[16];
+            tmem_ld16(sj, o);
+            tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < c; ++k) {
-              uint32_t o[16];
-              tmem_ld16(s_addr + k * 16, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float lo = __uint_as_float(o[i] << 16) * alpha, hi2 = __uint_as_float(o[i] & 0xffff0000u) * alpha;
-                o[i] = pack_bf16(lo, hi2);
-              }
-              tmem_st16(s_addr + k * 16, o);
+            for (int i = 0; i < 16; ++i) {
+              const float lo = __uint_as_float(o[i] << 16) * alpha, hi2 = __uint_as_float(o[i] & 0xffff0000u) * alpha;
+              o[i] = pack_bf16(lo, hi2);
             }
+            tmem_st16(sj, o);
             const uint64_t ap = pk2(alpha, alpha);
             ls2[0] = mul2(ls2[0], ap);
             ls2[1] = mul2(ls2[1], ap);
@@ -467,7 +458,7 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             const uint64_t vp = pk2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1]));
             uint64_t yp;
             if (RELPOS)
-              yp = add2(fma2(vp, c1p, pk2(tw[RELPOS ? (c & 1) * 32 + 2 * i : 0], tw[RELPOS ? (c & 1) * 32 + 2 * i + 1 : 0])), dp);
+              yp = add2(fma2(vp, c1p, pk2(tw[RELPOS ? c * 32 + 2 * i : 0], tw[RELPOS ? c * 32 + 2 * i + 1 : 0])), dp);
             else
               yp = fma2(vp, c1p, dp);
             float a0, a1;
@@ -479,22 +470,21 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         ls2[0] = add2(ls2[0], cs2[0]);
         ls2[1] = add2(ls2[1], cs2[1]);
-        tmem_st16(s_addr + c * 16, pk);
-        if (c < 3) tmem_ld_wait();  // chunk c + 1 has landed
+        // P chunk c (16 columns of bf16 pairs) overwrites score columns [16c, 16c+16) of chunk 0, which is in registers
+        tmem_st16(sj + c * 16, pk);
       }
-      if (q4 == 0 && lane == 0) F3_TRACE(t, j, 4);
-      if (TURNS && (t == 0 || j + 1 < nk)) named_bar_arrive(3 - t, 256);  // hand the MUFU to the other tile
       {
         float s0, s1, s2, s3;
         unpk2(ls2[0], s0, s1);
         unpk2(ls2[1], s2, s3);
         l_run += (s0 + s1) + (s2 + s3);
       }
+      if (q4 == 0 && lane == 0) F4_TRACE(t, j, 2);
       tmem_st_wait();
-      if (q4 == 0 && lane == 0) F3_TRACE(t, j, 5);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
+      if (lane == 0) mbar_arrive(&p_full[t * 2 + (j & 1)]);
+      if (q4 == 0 && lane == 0) F4_TRACE(t, j, 3);
     }
     // ---- epilogue: O / l
     mbar_wait(&o_full[t], 0);
@@ -524,48 +514,44 @@ flash3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   }
 }
 
-template <int HD, bool RELPOS, bool TURNS>
-static int launch_flash3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
+template <int HD, bool RELPOS>
+static int launch_flash4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                          const FlashParams& p, cudaStream_t st) {
-  using Cfg = Flash3Cfg<HD, RELPOS>;
+  using Cfg = Flash4Cfg<HD, RELPOS>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(flash3_kernel<HD, RELPOS, TURNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+    if (cudaFuncSetAttribute(flash4_kernel<HD, RELPOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
         cudaSuccess)
       return WM_ERR_CUDA;
     attr_set = true;
   }
   dim3 grid(p.Tq / 256, p.H, p.B);
-  flash3_kernel<HD, RELPOS, TURNS><<<grid, F3_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, trel, p);
+  flash4_kernel<HD, RELPOS><<<grid, F4_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, trel, p);
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 
 // q tiles: box 128 rows; k/v tiles: box 128 rows; rel table [256,64]: box 16 rows
-int flash3_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
+int flash4_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                     const FlashParams& p, int hd, cudaStream_t st) {
   if (p.Tq % 256 != 0 || p.Tk % 128 != 0 || p.Tk < 128) return WM_ERR_SHAPE;
-  const bool turns = p.turns != 0;
   if (p.use_relpos) {
     if (p.Tq != 4096 || p.Tk != 4096) return WM_ERR_SHAPE;
-    if (hd == 64)
-      return turns ? launch_flash3<64, true, true>(tq, tk, tv, trel, p, st) : launch_flash3<64, true, false>(tq, tk, tv, trel, p, st);
-    if (hd == 80) return launch_flash3<80, true, true>(tq, tk, tv, trel, p, st);
+    if (hd == 64) return launch_flash4<64, true>(tq, tk, tv, trel, p, st);
+    if (hd == 80) return launch_flash4<80, true>(tq, tk, tv, trel, p, st);
     return WM_ERR_SHAPE;
   }
-  if (hd == 80) return launch_flash3<80, false, true>(tq, tk, tv, trel, p, st);
-  if (hd == 64)
-    return turns ? launch_flash3<64, false, true>(tq, tk, tv, trel, p, st) : launch_flash3<64, false, false>(tq, tk, tv, trel, p, st);
-  if (hd == 128)
-    return turns ? launch_flash3<128, false, true>(tq, tk, tv, trel, p, st) : launch_flash3<128, false, false>(tq, tk, tv, trel, p, st);
+  if (hd == 64) return launch_flash4<64, false>(tq, tk, tv, trel, p, st);
+  if (hd == 80) return launch_flash4<80, false>(tq, tk, tv, trel, p, st);
+  if (hd == 128) return launch_flash4<128, false>(tq, tk, tv, trel, p, st);
   return WM_ERR_SHAPE;
 }
 
 #ifdef WM_F3_TRACE
-int flash3_read_trace(unsigned long long* host_out) {
-  return cudaMemcpyFromSymbol(host_out, g_f3_trace, sizeof(g_f3_trace)) == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+int flash4_read_trace(unsigned long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_f4_trace, sizeof(g_f4_trace)) == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 #else
-int flash3_read_trace(unsigned long long*) { return WM_ERR_ARCH; }
+int flash4_read_trace(unsigned long long*) { return WM_ERR_ARCH; }
 #endif
 
 }  // namespace wm

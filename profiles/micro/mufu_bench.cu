@@ -113,6 +113,34 @@ __global__ void __launch_bounds__(256, 1) bench(float* out, long long* cycles, i
       asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(cs0));
       asm("mov.b64 {%0, %1}, %2;" : "=f"(s2), "=f"(s3) : "l"(cs1));
       acc[0] += s0 + s1 + s2 + s3 + ymax0 * 1e-30f + ymax1 * 1e-30f;
+    } else if (VARIANT == 10 || VARIANT == 11) {
+      // packed half-precision exponentials: y + d (FADD2) -> cvt.rn.f16x2.f32 -> ex2.approx.f16x2 (ONE MUFU per pair,
+      // result already packed for the P operand) -> row sum in f16x2 (HADD2), one conversion per 32 scores
+      //   10: f16x2    11: bf16x2
+      unsigned h0 = 0u, h1 = 0u;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        unsigned long long vp, dp, yd;
+        float a0, a1;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(vp) : "f"(y[2 * i]), "f"(y[2 * i + 1]));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(dp) : "f"(d));
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(yd) : "l"(vp), "l"(dp));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(yd));
+        unsigned hp, ep;
+        if (VARIANT == 10) {
+          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hp) : "f"(a1), "f"(a0));
+          asm("ex2.approx.f16x2 %0, %1;" : "=r"(ep) : "r"(hp));
+          if (i & 1) asm("add.rn.f16x2 %0, %0, %1;" : "+r"(h1) : "r"(ep));
+          else asm("add.rn.f16x2 %0, %0, %1;" : "+r"(h0) : "r"(ep));
+        } else {
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hp) : "f"(a1), "f"(a0));
+          asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(ep) : "r"(hp));
+          if (i & 1) asm("add.rn.bf16x2 %0, %0, %1;" : "+r"(h1) : "r"(ep));
+          else asm("add.rn.bf16x2 %0, %0, %1;" : "+r"(h0) : "r"(ep));
+        }
+        pk ^= ep;
+      }
+      acc[0] += __uint_as_float(h0 << 16) + __uint_as_float(h1 << 16);
     } else if (VARIANT == 5) {
 #pragma unroll
       for (int i = 0; i < 128; ++i) {
@@ -155,6 +183,8 @@ int main() {
     run<7>("v4 rel-pos chunk without FMNMX", w);
     run<8>("v4 rel-pos chunk, scalar FFMA/FADD", w);
     run<9>("v4 rel-pos chunk, no FMNMX, pinned", w);
+    run<10>("packed ex2.f16x2 path", w);
+    run<11>("packed ex2.bf16x2 path", w);
   }
   return 0;
 }

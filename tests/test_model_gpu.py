@@ -160,3 +160,26 @@ def test_errors_are_loud():
     t = tiles.to(DEV).requires_grad_(True)
     with pytest.raises(RuntimeError):  # training path not implemented
         model(NestedTensor(t, None), None)
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The captured step (wildlifemapper_b200/graph.py) replays exactly the eager kernels: bit-identical detections,
+    also for a second batch fed through the static input."""
+    from wildlifemapper_b200 import postprocess as pp
+    from wildlifemapper_b200.graph import GraphedDetector
+    model = build("vit_t", 51)
+    sizes = torch.tensor([[1024, 1024]] * 2, device=DEV)
+    det = GraphedDetector(model, batch=2, conf_thr=0.05, nms_score_thr=0.05, iou_thr=0.4)
+    for seed in (2, 5):
+        tiles = make_tiles(2, seed=seed).to(DEV)
+        with torch.no_grad():
+            out = model(NestedTensor(tiles, None), None)
+            packed, _l, _q, counts = pp.postprocess_packed(out["pred_logits"], out["pred_boxes"], sizes, 0.05)
+            keep_idx, keep_cnt = pp.nms_packed(packed, counts, score_thr=0.05, iou_threshold=0.4)
+        g_packed, g_counts, g_keep_idx, g_keep_cnt = det(tiles)
+        torch.cuda.synchronize()
+        assert torch.equal(g_counts, counts) and torch.equal(g_keep_cnt, keep_cnt)
+        for b in range(2):
+            n, k = int(counts[b]), int(keep_cnt[b])
+            assert torch.equal(g_packed[b, :n], packed[b, :n])
+            assert torch.equal(g_keep_idx[b, :k], keep_idx[b, :k])

@@ -203,7 +203,7 @@ def test_attn_flash_rising_maxima(hd, flash_version):
     assert (out.float() - ref).abs().max().item() < 3e-2
 
 
-@pytest.fixture(params=[4, 3, 2, 1])
+@pytest.fixture(params=[5, 4, 3, 2, 1])
 def flash_version(request):
     """All flash-attention kernel generations stay parity-checked (4 = default)."""
     from wildlifemapper_b200 import lib

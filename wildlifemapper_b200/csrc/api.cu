@@ -145,7 +145,7 @@ int wm_set_option(const char* name, int value) {
   return fail(WM_ERR_SHAPE, "wm_set_option: unknown option '%s'", n.c_str());
 }
 int wm_set_flash_version(int version) {
-  if (version < 1 || version > 4) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 1, 2, 3 or 4");
+  if (version < 1 || version > 5) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 1 .. 5");
   g_flash_version = version;
   return WM_OK;
 }
@@ -281,8 +281,9 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   if (q_col0 + H * hd > q_width || k_col0 + H * hd > k_width || v_col0 + H * hd > v_width) return fail(WM_ERR_SHAPE, "wm_attn_flash: columns");
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || !aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_attn_flash: alignment");
   if (B > 65535 || H > 65535) return fail(WM_ERR_SHAPE, "wm_attn_flash: grid too large");
+  const bool v5 = (g_flash_version == 5) && (Tq % 256 == 0);
   const bool v4 = (g_flash_version == 4) && (Tq % 256 == 0);
-  const bool v3 = (g_flash_version == 3 || v4) && (Tq % 256 == 0);  // (v4 shares v3's tensor maps)
+  const bool v3 = (g_flash_version == 3 || v4 || v5) && (Tq % 256 == 0);  // (v4 / v5 share v3's tensor maps)
   const bool v2 = (g_flash_version == 2) && (Tq % 256 == 0);
   const uint32_t kv_box = v2 ? 64 : 128;
   CUtensorMap tq, tk, tv, trel;
@@ -301,6 +302,7 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldo = (int)ldo;
   p.use_relpos = rel_table != nullptr;
   p.turns = g_flash_turns;
+  if (v5) return check_launch(wm::flash5_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v5)");
   if (v4) return check_launch(wm::flash4_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v4)");
   if (v3) return check_launch(wm::flash3_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v3)");
   if (v2) return check_launch(wm::flash2_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v2)");
@@ -308,7 +310,7 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
 }
 
 int wm_debug_flash_trace(uint64_t* host_out_3x64x4) {
-  const int rc = g_flash_version == 4 ? wm::flash4_read_trace(reinterpret_cast<unsigned long long*>(host_out_3x64x4))
+  const int rc = g_flash_version >= 4 ? wm::flash4_read_trace(reinterpret_cast<unsigned long long*>(host_out_3x64x4))
                                       : wm::flash3_read_trace(reinterpret_cast<unsigned long long*>(host_out_3x64x4));
   if (rc != WM_OK)
     return fail(WM_ERR_ARCH, "wm_debug_flash_trace: only available in the diagnostics build (-DWM_F3_TRACE)");

@@ -1,0 +1,526 @@
+// Flash attention v5 on tcgen05 / TMEM (sm_100a): global 64x64 attention with decomposed rel-pos bias and the HFC
+// cross-attention.  Same math and reference sites as attn_flash.cu (image_encoder.py:246-262, 347-383, 500-503) and the
+// same pipeline as v4 (attn_flash4.cu: two 128-query tiles per CTA, 64-key steps over double-buffered score tiles, P in
+// tensor memory, lazy rescaling), with TWICE the softmax warps: ncu on v4 shows 0.5 eligible warps per scheduler cycle
+// and the MUFU ~57 % busy -- two softmax warps per scheduler do not cover each other's dependency stalls, and ptxas
+// issues the exp2 of a chunk as one burst.  Here every query row is shared by TWO threads (16 softmax warps, four per
+// scheduler): thread `hf` of a row owns key columns [32 hf, 32 hf + 32) of every 64-key step.
+//   * the two threads of a row agree on the row maximum through a double-buffered shared-memory slot and a 64-thread
+//     named barrier per warp pair (which also orders the partner's P store behind this thread's score load);
+//   * each keeps its own partial row sum (added in the epilogue), half of bias_w (32 registers) and stores half of P;
+//   * registers: 640 threads, setmaxnreg 40 (producer / MMA warpgroup) and 112 (softmax warpgroups).
+//
+//
+// MEASURED (round 1, B200, ViT-B batch 32): 16.4 ms per step against 15.0 ms for v4 -- the per-step pair barrier and the
+// tighter register budget cost more than the extra warps recover.  Not the default; selectable for A/B ("flash_version" 5).
+//
+//   warp 0       TMA producer          warp 1  tcgen05.mma issuer          warp 2  TMEM allocator
+//   warps 4-19   softmax: warp = 4 + 8 tile + 4 hf + lane quarter
+#include "common.cuh"
+#include "wm_internal.h"
+
+namespace wm {
+
+constexpr int F5_THREADS = 640;  // 4 producer / MMA / allocator warps + 16 softmax warps
+constexpr float F5_LOG2E = 1.4426950408889634f;
+constexpr float F5_TAU = 8.0f;  // lazy-rescale threshold (log2 units): p <= 2^8 between rescales
+
+template <int HD, bool RELPOS>
+struct Flash5Cfg {
+  static_assert(HD % 16 == 0 && HD >= 64 && HD <= 128, "head dim");
+  static_assert(!RELPOS || HD <= 96, "rel-pos variant: tensor-memory budget");
+  static constexpr int SUB = (HD + 63) / 64;       // 64-column (128-byte) sub-tiles per operand row (a partial second
+                                                   // sub-tile -- head dim 80 -- is loaded 64 wide; only HD columns are used)
+  static constexpr int KSTEPS = HD / 16;           // K = 16 MMA steps over the head dim
+  static constexpr int STAGES = (SUB == 1) ? 4 : 2;
+  static constexpr int TILE_BYTES = SUB * 16384;   // 128 rows (queries or keys) x SUB x 128 B
+  static constexpr int OFF_Q = 0;                  // 2 query tiles
+  static constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + STAGES * TILE_BYTES;
+  // RELPOS prologue: Rw [128 rows] + 2 x Rh slice [80 rows] (x SUB sub-tiles); afterwards its first 32 KB are fp32
+  // scatter scratch.  Head dim 64: own region.  Larger head dims: the tables ALIAS K stage 1 and the V stages, whose
+  // first loads wait for the prologue (t_done).
+  static constexpr bool TAB_ALIAS = RELPOS && SUB > 1;
+  static constexpr int TAB_BYTES = RELPOS ? SUB * (16384 + 2 * 10240) : 0;
+  static constexpr int OFF_TAB = TAB_ALIAS ? OFF_K + TILE_BYTES : OFF_V + STAGES * TILE_BYTES;
+  static_assert(!TAB_ALIAS || TAB_BYTES <= (2 * STAGES - 1) * TILE_BYTES, "aliased table region");
+  static constexpr int OFF_BAR = OFF_V + STAGES * TILE_BYTES + (TAB_ALIAS ? 0 : TAB_BYTES);
+  static constexpr int OFF_XCH = OFF_BAR + 256;  // fp32 [2 slots][2 tiles][2 halves][128 rows] row-maximum / row-sum exchange
+  static constexpr int SMEM_BYTES = OFF_XCH + 4096 + 1024;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  // TMEM columns: S_t buffer b at 128 t + 64 b (P = bf16 pairs in its first 32 columns), O_t at 256 + HD t, then T_h:
+  //   head dim 64: fp32, 64 columns per tile (+ column 64 in a register);  larger: fp16 pairs, 33 of 40 columns per tile
+  static constexpr int COL_O = 256;
+  static constexpr int COL_TH = COL_O + 2 * HD;
+  static constexpr bool TH_PACKED = HD > 64;
+  static constexpr int TH_STRIDE = TH_PACKED ? 40 : 64;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(COL_TH + (RELPOS ? 2 * TH_STRIDE : 0) <= 512, "TMEM budget");
+};
+
+template <int HD, bool RELPOS>
+__global__ void __launch_bounds__(F5_THREADS, 1)
+flash5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_rel,
+              const FlashParams p) {
+  using Cfg = Flash5Cfg<HD, RELPOS>;
+  constexpr int NS = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [4]
+  uint64_t* k_empty = bars + 5;   // [4]
+  uint64_t* v_full = bars + 9;    // [4]
+  uint64_t* v_empty = bars + 13;  // [4]
+  uint64_t* s_full = bars + 17;   // [2 tiles][2 buffers]  S_t(j) complete
+  uint64_t* p_full = bars + 21;   // [2 tiles][2 buffers]  P_t(j) stored to TMEM by the 4 warps of tile t
+  uint64_t* pv_done = bars + 25;  // [2]  P_t(j) V complete (only waited on by the rare rescale path)
+  uint64_t* o_full = bars + 27;   // [2]
+  uint64_t* t_full = bars + 29;   // rel-pos table products complete
+  uint64_t* t_done = bars + 30;   // ... and drained out of the S / O columns by the 8 softmax warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
+
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int nk = p.Tk / 128;  // 128-key TMA tiles
+  const int ns = p.Tk / 64;   // 64-key softmax / MMA steps
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&o_full[i], 1);
+    }
+    mbar_init(t_full, 1);
+    mbar_init(t_done, 16);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    setmaxnreg_dec<32>();  // 640 threads start at 96 registers: 128 x 64 freed = 512 x 16 needed by the softmax warps
+    // Producer and MMA roles: the WHOLE warp runs the control flow (uniform branches, every lane polls the
+    // barriers); one elected lane issues the TMA / tcgen05 instructions.
+    if (warp == 0) {
+      // ------------------------------------------------------------ TMA producer
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES + Cfg::TAB_BYTES);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int s = 0; s < Cfg::SUB; ++s)
+            tma_load_2d(smem + Cfg::OFF_Q + t * Cfg::TILE_BYTES + s * 16384, &tmap_q, q_full, p.q_col0 + h * HD + s * 64,
+                        b * p.Tq + m0 + t * 128);
+        if (RELPOS) {
+          // table tensor [256,HD]: rows 0..126 rel_pos_h, 128..254 rel_pos_w.  Box = 64 columns x 16 rows.
+          const int qi0 = m0 >> 6;  // first image row of this CTA (4 rows: 2 per query tile)
+          for (int sb = 0; sb < Cfg::SUB; ++sb) {
+            for (int i = 0; i < 8; ++i)
+              tma_load_2d(smem + Cfg::OFF_TAB + sb * 16384 + i * 2048, &tmap_rel, q_full, sb * 64, 128 + 16 * i);
+            for (int t = 0; t < 2; ++t)
+              for (int i = 0; i < 5; ++i)
+                tma_load_2d(smem + Cfg::OFF_TAB + Cfg::SUB * 16384 + (t * Cfg::SUB + sb) * 10240 + i * 2048, &tmap_rel, q_full,
+                            sb * 64, qi0 + 2 * t + 16 * i);
+          }
+        }
+      }
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nk; ++j) {
+        if (Cfg::TAB_ALIAS && j == 1) mbar_wait(t_done, 0);  // K stage 1 and the V stages hold the tables until then
+        mbar_wait(&k_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+          for (int s = 0; s < Cfg::SUB; ++s)
+            tma_load_2d(smem + Cfg::OFF_K + st * Cfg::TILE_BYTES + s * 16384, &tmap_k, &k_full[st],
+                        p.k_col0 + h * HD + s * 64, b * p.Tk + j * 128);
+        }
+        if (Cfg::TAB_ALIAS && j == 0) mbar_wait(t_done, 0);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+          for (int s = 0; s < Cfg::SUB; ++s)
+            tma_load_2d(smem + Cfg::OFF_V + st * Cfg::TILE_BYTES + s * 16384, &tmap_v, &v_full[st],
+                        p.v_col0 + h * HD + s * 64, b * p.Tk + j * 128);
+        }
+        __syncwarp();
+        if (++st == NS) { st = 0; ph ^= 1; }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);  // A = P from TMEM (K-major), V is MN-major
+      const bool leader = elect_one();  // the same lane issues every tcgen05.mma / tcgen05.commit
+      const uint32_t sq = smem_u32(smem + Cfg::OFF_Q);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      if (RELPOS) {
+        constexpr uint32_t idesc_tw = make_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc_th = make_idesc_bf16(128, Cfg::TH_PACKED ? 80 : 64, 0, 0);
+        constexpr uint32_t idesc_tx = make_idesc_bf16(128, 16, 0, 0);
+        const uint32_t stab = smem_u32(smem + Cfg::OFF_TAB);
+        // T_w(t) -> S_t columns.  Head dim 64: T_h(t)[0..63] -> resident columns, T_h(t)[64..79] -> scratch in the O
+        // columns.  Larger head dims: T_h(t)[0..79] -> O_t columns (scratch; the softmax warps repack it as fp16 pairs).
+        if (leader) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+#pragma unroll
+            for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+              const uint32_t koff = (ks & 3) * 32;
+              const uint32_t srh = stab + Cfg::SUB * 16384 + (t * Cfg::SUB + (ks >> 2)) * 10240 + koff;
+              const uint64_t ad = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES + (ks >> 2) * 16384 + koff, 16, 1024);
+              umma_bf16(tmem_base + t * 128, ad, make_sdesc_sw128(stab + (ks >> 2) * 16384 + koff, 16, 1024), idesc_tw, ks != 0);
+              if (Cfg::TH_PACKED) {
+                umma_bf16(tmem_base + Cfg::COL_O + t * HD, ad, make_sdesc_sw128(srh, 16, 1024), idesc_th, ks != 0);
+              } else {
+                umma_bf16(tmem_base + Cfg::COL_TH + t * 64, ad, make_sdesc_sw128(srh, 16, 1024), idesc_th, ks != 0);
+                umma_bf16(tmem_base + Cfg::COL_O + t * 16, ad, make_sdesc_sw128(srh + 8192, 16, 1024), idesc_tx, ks != 0);
+              }
+            }
+          }
+          umma_commit(t_full);
+        }
+        __syncwarp();
+        mbar_wait(t_done, 0);  // both warpgroups have drained the scratch out of the S / O columns
+        tc_fence_after();
+      }
+      // S_t(step) = Q_t K(step)^T (128 x 64 x HD) into score buffer (step & 1) of tile t; K rows of step: half (step & 1)
+      // of stage (step / 2) % NS.  (MMAs that accumulate into the same tensor-memory tile are serialised by the
+      // accumulator round trip, ~90 cycles per 128 x 64 x 16 step; issuing the two tiles' chains interleaved shortens
+      // the issue time but forces the tiles into lockstep and measured slower end to end: profiles/r01u_flash4_*.txt.)
+      auto issue_s = [&](int t, int step) {
+        if (leader) {
+          const int kst = (step >> 1) % NS;
+          const uint64_t qd = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES, 16, 1024);
+          const uint64_t kd = make_sdesc_sw128(smem_u32(smem + Cfg::OFF_K + kst * Cfg::TILE_BYTES) + (step & 1) * 8192, 16, 1024);
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+            const uint32_t off = (uint32_t)((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);  // address field is bytes >> 4
+            umma_bf16(tmem_base + t * 128 + (step & 1) * 64, qd + off, kd + off, idesc_s, ks != 0);
+          }
+          umma_commit(&s_full[t * 2 + (step & 1)]);
+        }
+        __syncwarp();
+      };
+      // two steps ahead of the softmax (both from K tile 0)
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      issue_s(0, 1);
+      issue_s(1, 1);
+      if (leader) umma_commit(&k_empty[0]);
+      __syncwarp();
+      for (int j = 0; j < ns; ++j) {
+        const int vst = (j >> 1) % NS;
+        const uint32_t vph = (uint32_t)((j >> 1) / NS) & 1u;
+        const bool more = j + 2 < ns;
+        const uint32_t sv = smem_u32(smem + Cfg::OFF_V + vst * Cfg::TILE_BYTES) + (j & 1) * 8192;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_full[t * 2 + (j & 1)], (uint32_t)(j >> 1) & 1u);
+          if (t == 0) {
+            if ((j & 1) == 0) mbar_wait(&v_full[vst], vph);
+            if (more && (j & 1) == 0) {  // step j + 2 opens K tile (j + 2) / 2
+              const int kt = (j + 2) >> 1;
+              mbar_wait(&k_full[kt % NS], (uint32_t)(kt / NS) & 1u);
+            }
+          }
+          tc_fence_after();
+          if (leader) {
+            const uint64_t vd = make_sdesc_sw128(sv, 16384, 1024);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)  // 64 keys, 16 per MMA; P: 8 TMEM columns per step; V: 2048 B per step
+              umma_bf16_ts(tmem_base + Cfg::COL_O + t * HD, tmem_base + t * 128 + (j & 1) * 64 + ks * 8,
+                           vd + (uint32_t)(ks * (2048 >> 4)), idesc_pv, (j | ks) != 0);
+            umma_commit(&pv_done[t]);
+            if (j == ns - 1) umma_commit(&o_full[t]);
+          }
+          __syncwarp();
+          if (more) issue_s(t, j + 2);  // reuses the score buffer step j just released (behind its P V in the pipe)
+        }
+        if (leader) {
+          if (j & 1) umma_commit(&v_empty[vst]);                       // both halves of the V tile consumed
+          if (more && (j & 1)) umma_commit(&k_empty[((j + 2) >> 1) % NS]);  // both halves of K tile (j + 2) / 2 issued
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax / correction / output
+    setmaxnreg_inc<112>();
+    const int t = (warp - 4) >> 3;        // query tile
+    const int hf = ((warp - 4) >> 2) & 1; // which half of the key columns of a step
+    const int q4 = warp & 3;              // TMEM lane quarter
+    const int r = q4 * 32 + lane;   // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const uint32_t s_addr = lane_addr + t * 128;
+    const uint32_t o_addr = lane_addr + Cfg::COL_O + t * HD;
+    const float c1 = p.scale * F5_LOG2E;
+    float tw[RELPOS ? 32 : 1];            // bias_w of key columns [32 hf, 32 hf + 32)
+    float* xch = reinterpret_cast<float*>(smem + Cfg::OFF_XCH);
+    const int pair_bar = 1 + t * 4 + q4;  // named barrier of the two warps that share these 32 rows
+    float bh64 = 0.0f;                                            // T_h column 64 (only needed by key row 0)
+    const int hi = r >> 6;                                        // image row of this query inside the tile (warp-uniform)
+    const uint32_t th_addr = lane_addr + Cfg::COL_TH + t * Cfg::TH_STRIDE;  // bias_h[kh] = T_h[hi + 63 - kh]
+
+    if (RELPOS) {
+      const int qj = (m0 + t * 128 + r) & 63;
+      mbar_wait(t_full, 0);
+      tc_fence_after();
+      if (Cfg::TH_PACKED && hf == 0) {
+        // T_h(t)[0..79] sits in the O_t columns as fp32: keep [0..64] as fp16 pairs (x log2 e) in the resident columns
+        uint32_t a[32], bq[32], cq[16];
+        tmem_ld32(o_addr, a);
+        tmem_ld32(o_addr + 32, bq);
+        tmem_ld16(o_addr + 64, cq);
+        tmem_ld_wait();
+        uint32_t pkh[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          pkh[i] = pack_f16(__uint_as_float(a[2 * i]) * F5_LOG2E, __uint_as_float(a[2 * i + 1]) * F5_LOG2E);
+          pkh[16 + i] = pack_f16(__uint_as_float(bq[2 * i]) * F5_LOG2E, __uint_as_float(bq[2 * i + 1]) * F5_LOG2E);
+        }
+        tmem_st32(th_addr, pkh);
+        tmem_st1(th_addr + 32, pack_f16(__uint_as_float(cq[0]) * F5_LOG2E, 0.0f));
+        tmem_st_wait();
+      } else if (!Cfg::TH_PACKED) {
+        const uint32_t x = tmem_ld1(lane_addr + Cfg::COL_O + t * 16);
+        tmem_ld_wait();
+        bh64 = __uint_as_float(x) * F5_LOG2E;
+      }
+      // bias_w[kw] = T_w[qj + 63 - kw] for this thread's 32 key columns: scatter through an XOR-swizzled 32-float smem
+      // row per query row; the two warps of a pair use the row one after the other
+      float* scr = reinterpret_cast<float*>(smem + Cfg::OFF_TAB) + ((t * 128 + r) << 5);
+#pragma unroll 1
+      for (int turn = 0; turn < 2; ++turn) {
+        if (turn == hf) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(s_addr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int kw = qj + 63 - (c * 32 + i) - hf * 32;
+              if (kw >= 0 && kw < 32) scr[((((kw >> 2) ^ (r & 7)) << 2) | (kw & 3))] = __uint_as_float(v[i]) * F5_LOG2E;
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 w = *reinterpret_cast<const float4*>(scr + ((g ^ (r & 7)) << 2));
+            tw[RELPOS ? 4 * g : 0] = w.x; tw[RELPOS ? 4 * g + 1 : 0] = w.y;
+            tw[RELPOS ? 4 * g + 2 : 0] = w.z; tw[RELPOS ? 4 * g + 3 : 0] = w.w;
+          }
+        }
+        tc_fence_before();
+        named_bar_sync(pair_bar, 64);
+        tc_fence_after();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_done);
+    }
+
+    float m_ref = -INFINITY, l_run = 0.0f;  // m_ref is kept identical in the two threads of a row; l_run is this half's sum
+    for (int j = 0; j < ns; ++j) {  // one step = 64 keys = key row j of the 64x64 grid
+      const uint32_t sj = s_addr + (j & 1) * 64;  // this step's score buffer; P = bf16 pairs over its first 32 columns
+      mbar_wait(&s_full[t * 2 + (j & 1)], (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(sj + hf * 32, v);
+      float bh = 0.0f;
+      if (RELPOS) {
+        const int c0 = hi + 63 - j;  // T_h index of key row j
+        if (Cfg::TH_PACKED) {
+          const uint32_t a0 = tmem_ld1(th_addr + (c0 >> 1));
+          tmem_ld_wait();
+          bh = unpack_f16(a0, c0 & 1);
+        } else {
+          const uint32_t a0 = tmem_ld1(th_addr + (c0 > 63 ? 63 : c0));
+          tmem_ld_wait();
+          bh = (c0 > 63) ? bh64 : __uint_as_float(a0) * F5_LOG2E;
+        }
+      } else {
+        tmem_ld_wait();
+      }
+      // ---- optimistic pass over this thread's 32 scores against the current reference maximum
+      const uint64_t c1p = pk2(c1, c1);
+      float d = RELPOS ? bh - m_ref : -m_ref;  // +inf while m_ref = -inf: the first step always takes the exact path
+      float ymax[2] = {-INFINITY, -INFINITY};
+      uint64_t cs2[2] = {0ull, 0ull};
+      uint32_t pk[16];
+      {
+        const uint64_t dp = pk2(d, d);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint64_t vp = pk2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+          uint64_t yp;
+          if (RELPOS) {
+            const uint64_t y2 = fma2(vp, c1p, pk2(tw[RELPOS ? 2 * i : 0], tw[RELPOS ? 2 * i + 1 : 0]));
+            float y0, y1;
+            unpk2(y2, y0, y1);
+            ymax[0] = fmaxf(ymax[0], y0);
+            ymax[1] = fmaxf(ymax[1], y1);
+            yp = add2(y2, dp);
+          } else {
+            ymax[0] = fmaxf(ymax[0], __uint_as_float(v[2 * i]));  // raw scores: c1 > 0
+            ymax[1] = fmaxf(ymax[1], __uint_as_float(v[2 * i + 1]));
+            yp = fma2(vp, c1p, dp);
+          }
+          float a0, a1;
+          unpk2(yp, a0, a1);
+          const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+          cs2[i & 1] = add2(cs2[i & 1], pk2(e0, e1));
+          pk[i] = pack_bf16(e0, e1);
+        }
+      }
+      // ---- the two threads of a row agree on the maximum of the step (slot j & 1: a thread is never two steps ahead of
+      // its partner).  The barrier also orders the partner's P store (columns 16..31 of the buffer when hf = 1) behind
+      // this thread's score load.
+      const float m_half = RELPOS ? fmaxf(ymax[0], ymax[1]) + bh : fmaxf(ymax[0], ymax[1]) * c1;
+      float* slot = xch + (((j & 1) * 2 + t) * 2) * 128;
+      slot[hf * 128 + r] = m_half;
+      tc_fence_before();
+      named_bar_sync(pair_bar, 64);
+      tc_fence_after();
+      const float m_step = fmaxf(m_half, slot[(hf ^ 1) * 128 + r]);
+      const bool need = m_step > m_ref + F5_TAU;
+      if (__any_sync(0xffffffffu, need)) {
+        // ---- exact path (rare after the first step): raise the reference maximum (identically in both threads of the row;
+        // `need` is a function of m_step and m_ref only, so both warps of the pair take this branch together).  O is
+        // rescaled by the hf = 0 thread; P_t(j-1) V is the last MMA that touches O_t before p_full(j).
+        const float m_new = need ? m_step : m_ref;
+        const float alpha = ex2_approx(m_ref - m_new);  // 1 for rows that did not need it, 0 on the very first step
+        if (j > 0 && hf == 0) {
+          mbar_wait(&pv_done[t], (uint32_t)(j - 1) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) {
+            uint32_t o[16];
+            tmem_ld16(o_addr + k * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(o_addr + k * 16, o);
+          }
+        }
+        l_run *= alpha;
+        m_ref = m_new;
+        d = RELPOS ? bh - m_ref : -m_ref;
+        cs2[0] = 0ull;
+        cs2[1] = 0ull;
+        const uint64_t dp = pk2(d, d);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint64_t vp = pk2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+          uint64_t yp;
+          if (RELPOS)
+            yp = add2(fma2(vp, c1p, pk2(tw[RELPOS ? 2 * i : 0], tw[RELPOS ? 2 * i + 1 : 0])), dp);
+          else
+            yp = fma2(vp, c1p, dp);
+          float a0, a1;
+          unpk2(yp, a0, a1);
+          const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+          cs2[i & 1] = add2(cs2[i & 1], pk2(e0, e1));
+          pk[i] = pack_bf16(e0, e1);
+        }
+      }
+      {
+        float s0, s1, s2, s3;
+        unpk2(cs2[0], s0, s1);
+        unpk2(cs2[1], s2, s3);
+        l_run += (s0 + s1) + (s2 + s3);
+      }
+      tmem_st16(sj + hf * 16, pk);  // P columns [16 hf, 16 hf + 16) = keys [32 hf, 32 hf + 32) of this step
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t * 2 + (j & 1)]);
+    }
+    // ---- epilogue: O / (l_0 + l_1); each thread of a row stores half of the head dim
+    {
+      float* slot = xch + ((ns & 1) * 2 + t) * 2 * 128;  // (slot not used by the last step)
+      slot[hf * 128 + r] = l_run;
+      named_bar_sync(pair_bar, 64);
+      l_run += slot[(hf ^ 1) * 128 + r];
+    }
+    mbar_wait(&o_full[t], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    constexpr int HALF = HD / 2;  // 32, 40 or 64 columns per thread, in chunks of 8
+    __nv_bfloat16* dst = p.out + (size_t)(b * p.Tq + m0 + t * 128 + r) * p.ldo + h * HD + hf * HALF;
+#pragma unroll
+    for (int c = 0; c < HALF / 8; ++c) {
+      uint32_t o[8];
+      tmem_ld8(o_addr + hf * HALF + c * 8, o);
+      tmem_ld_wait();
+      *reinterpret_cast<uint4*>(dst + c * 8) =
+          make_uint4(pack_bf16(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l),
+                     pack_bf16(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l),
+                     pack_bf16(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l),
+                     pack_bf16(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l));
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int HD, bool RELPOS>
+static int launch_flash5(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
+                         const FlashParams& p, cudaStream_t st) {
+  using Cfg = Flash5Cfg<HD, RELPOS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(flash5_kernel<HD, RELPOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+        cudaSuccess)
+      return WM_ERR_CUDA;
+    attr_set = true;
+  }
+  dim3 grid(p.Tq / 256, p.H, p.B);
+  flash5_kernel<HD, RELPOS><<<grid, F5_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, trel, p);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// q tiles: box 128 rows; k/v tiles: box 128 rows; rel table [256,64]: box 16 rows
+int flash5_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
+                    const FlashParams& p, int hd, cudaStream_t st) {
+  if (p.Tq % 256 != 0 || p.Tk % 128 != 0 || p.Tk < 128) return WM_ERR_SHAPE;
+  if (p.use_relpos) {
+    if (p.Tq != 4096 || p.Tk != 4096) return WM_ERR_SHAPE;
+    if (hd == 64) return launch_flash5<64, true>(tq, tk, tv, trel, p, st);
+    if (hd == 80) return launch_flash5<80, true>(tq, tk, tv, trel, p, st);
+    return WM_ERR_SHAPE;
+  }
+  if (hd == 64) return launch_flash5<64, false>(tq, tk, tv, trel, p, st);
+  if (hd == 80) return launch_flash5<80, false>(tq, tk, tv, trel, p, st);
+  if (hd == 128) return launch_flash5<128, false>(tq, tk, tv, trel, p, st);
+  return WM_ERR_SHAPE;
+}
+
+}  // namespace wm

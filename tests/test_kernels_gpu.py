@@ -184,6 +184,22 @@ def test_attn_flash_plain(hd, H, T, flash_version):
     assert (out.float() - ref).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("Tq,Tk,hd", [(900, 900, 64), (900, 4096, 64), (4096, 900, 64), (51, 130, 64), (300, 77, 128)])
+def test_attn_flash_ragged(Tq, Tk, hd):
+    """Query / key counts that are not multiples of the tile sizes (decoder attention with 900 queries): rows beyond Tq
+    are not stored, keys beyond Tk are masked (v4 kernel)."""
+    B, H = 2, 8
+    q = rnd(B * Tq, H * hd, seed=50)
+    k, v = rnd(B * Tk, H * hd, seed=51), rnd(B * Tk, H * hd, seed=52)
+    out = torch.full((B * Tq + 7, H * hd), 7.0, device=DEV, dtype=torch.bfloat16)  # canary rows behind the last query
+    scale = 0.25
+    ops.attn_flash(q, 0, k, 0, v, 0, None, out, B, H, Tq, Tk, hd, scale)
+    sp = lambda t, T: t.view(B, T, H, hd).transpose(1, 2)
+    ref = ref_attention(sp(q, Tq), sp(k, Tk), sp(v, Tk), scale).transpose(1, 2).reshape(B * Tq, H * hd)
+    assert (out[:B * Tq].float() - ref).abs().max().item() < 2e-2
+    assert (out[B * Tq:] == 7.0).all()
+
+
 @pytest.mark.parametrize("hd", [64, 128])
 def test_attn_flash_rising_maxima(hd, flash_version):
     """Scores that keep growing along the key axis force the lazy-rescale path (reference maximum raised, O and l

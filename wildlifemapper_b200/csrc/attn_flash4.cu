@@ -92,8 +92,11 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
-  const int nk = p.Tk / 128;  // 128-key TMA tiles
-  const int ns = p.Tk / 64;   // 64-key softmax / MMA steps
+  // Tq and Tk need not be multiples of the tile sizes (decoder attention, 900 queries): query rows >= Tq are computed
+  // from whatever the TMA box finds there and never stored; key columns >= Tk are masked to -inf in the softmax (their
+  // V rows are multiplied by exact zeros).
+  const int nk = (p.Tk + 127) / 128;  // 128-key TMA tiles
+  const int ns = (p.Tk + 63) / 64;    // 64-key softmax / MMA steps
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -375,6 +378,14 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       } else {
         tmem_ld_wait();
       }
+      if (!RELPOS && (j + 1) * 64 > p.Tk) {  // ragged last step: keys >= Tk get a score of -inf (exp2 -> 0)
+        const int nvalid = p.Tk - j * 64;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= nvalid) v[0][i] = 0xff800000u;
+          if (32 + i >= nvalid) v[1][i] = 0xff800000u;
+        }
+      }
       uint64_t ls2[2] = {0ull, 0ull};  // this step's row sum (relative to m_ref): 2 packed pairs = 4 independent chains
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -491,6 +502,7 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     __nv_bfloat16* dst = p.out + (size_t)(b * p.Tq + m0 + t * 128 + r) * p.ldo + h * HD;
+    const bool row_ok = m0 + t * 128 + r < p.Tq;
 #pragma unroll
     for (int c = 0; c < HD / 16; ++c) {
       uint32_t o[16];
@@ -499,7 +511,7 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       uint4* d4 = reinterpret_cast<uint4*>(dst + c * 16);
 #pragma unroll
       for (int g = 0; g < 2; ++g)
-        d4[g] = make_uint4(pack_bf16(__uint_as_float(o[8 * g]) * inv_l, __uint_as_float(o[8 * g + 1]) * inv_l),
+        if (row_ok) d4[g] = make_uint4(pack_bf16(__uint_as_float(o[8 * g]) * inv_l, __uint_as_float(o[8 * g + 1]) * inv_l),
                            pack_bf16(__uint_as_float(o[8 * g + 2]) * inv_l, __uint_as_float(o[8 * g + 3]) * inv_l),
                            pack_bf16(__uint_as_float(o[8 * g + 4]) * inv_l, __uint_as_float(o[8 * g + 5]) * inv_l),
                            pack_bf16(__uint_as_float(o[8 * g + 6]) * inv_l, __uint_as_float(o[8 * g + 7]) * inv_l));
@@ -525,7 +537,7 @@ static int launch_flash4(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
       return WM_ERR_CUDA;
     attr_set = true;
   }
-  dim3 grid(p.Tq / 256, p.H, p.B);
+  dim3 grid((p.Tq + 255) / 256, p.H, p.B);
   flash4_kernel<HD, RELPOS><<<grid, F4_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, trel, p);
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
@@ -533,7 +545,7 @@ static int launch_flash4(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
 // q tiles: box 128 rows; k/v tiles: box 128 rows; rel table [256,64]: box 16 rows
 int flash4_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                     const FlashParams& p, int hd, cudaStream_t st) {
-  if (p.Tq % 256 != 0 || p.Tk % 128 != 0 || p.Tk < 128) return WM_ERR_SHAPE;
+  if (p.Tq < 1 || p.Tk < 1) return WM_ERR_SHAPE;
   if (p.use_relpos) {
     if (p.Tq != 4096 || p.Tk != 4096) return WM_ERR_SHAPE;
     if (hd == 64) return launch_flash4<64, true>(tq, tk, tv, trel, p, st);

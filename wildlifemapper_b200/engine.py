@@ -278,6 +278,19 @@ class DecoderEngine:
             for n in ("q", "k", "v", "out"):
                 w[f"{dst}.{n}_w"] = _bf(g(f"{src}.{n}_proj.weight"))
                 w[f"{dst}.{n}_b"] = _f32(g(f"{src}.{n}_proj.bias"))
+            # head-padded copies for the tcgen05 flash kernel (large query counts): every head of 16 / 32 channels gets its
+            # own 64-column slot, the padding rows / columns are zero, so q.k and the out projection are unchanged
+            C = w[f"{dst}.q_w"].shape[0]
+            hd = C // 8
+            idx = (torch.arange(8, device=dev)[:, None] * 64 + torch.arange(hd, device=dev)[None, :]).reshape(-1)
+            for n in ("q", "k", "v"):
+                wp = torch.zeros(512, 256, device=dev, dtype=torch.bfloat16)
+                bp = torch.zeros(512, device=dev, dtype=torch.float32)
+                wp[idx], bp[idx] = w[f"{dst}.{n}_w"], w[f"{dst}.{n}_b"]
+                w[f"{dst}.{n}p_w"], w[f"{dst}.{n}p_b"] = wp, bp
+            wo = torch.zeros(256, 512, device=dev, dtype=torch.bfloat16)
+            wo[:, idx] = w[f"{dst}.out_w"]
+            w[f"{dst}.outp_w"] = wo
 
         for i in range(2):
             L = f"layers.{i}."
@@ -300,22 +313,31 @@ class DecoderEngine:
                 w[f"{head}.{i}_w"] = _bf(sd[f"{head}.layers.{i}.weight"].to(dev))
                 w[f"{head}.{i}_b"] = _f32(sd[f"{head}.layers.{i}.bias"].to(dev))
 
-    def _attention(self, pre: str, q_in, k_in, v_in, B: int, Tq: int, Tk: int, name: str) -> torch.Tensor:
-        """transformer.py:218-240: projections -> 8-head attention (returns the pre-out_proj rows, bf16)."""
+    FLASH_MIN_TOKENS = 256  # query counts from here on go through the tcgen05 flash kernel (head dims padded to 64)
+
+    def _attention(self, pre: str, q_in, k_in, v_in, B: int, Tq: int, Tk: int, name: str):
+        """transformer.py:218-240: projections -> 8-head attention.  Returns (pre-out_proj rows bf16, out_proj weight).
+        Small query counts (the reference's 51): thread-per-query kernel on the 16 / 32-channel heads.  Large ones (dense
+        herds, 900 queries): the projections write head-padded [*, 8 x 64] rows and the v4 flash kernel does the rest."""
         w, ws = self.w, self.ws
-        C = w[pre + ".q_w"].shape[0]
         bf = torch.bfloat16
-        qh = ws.get(name + ".qh", (B * Tq, C), bf)
-        kh = ws.get(name + ".kh", (B * Tk, C), bf)
-        vh = ws.get(name + ".vh", (B * Tk, C), bf)
-        _gemm(q_in, w[pre + ".q_w"], w[pre + ".q_b"], out_bf16=qh)
-        _gemm(k_in, w[pre + ".k_w"], w[pre + ".k_b"], out_bf16=kh)
-        _gemm(v_in, w[pre + ".v_w"], w[pre + ".v_b"], out_bf16=vh)
-        o = ws.get(name + ".o", (B * Tq, C), bf)
+        C = w[pre + ".q_w"].shape[0]
         hd = C // 8
-        ops.attn_small(qh, kh, vh, o, B, 8, Tq, Tk, hd, 1.0 / math.sqrt(hd))
+        flash = min(Tq, Tk) >= self.FLASH_MIN_TOKENS
+        sfx, Cp = ("p", 512) if flash else ("", C)
+        qh = ws.get(name + ".qh" + sfx, (B * Tq, Cp), bf)
+        kh = ws.get(name + ".kh" + sfx, (B * Tk, Cp), bf)
+        vh = ws.get(name + ".vh" + sfx, (B * Tk, Cp), bf)
+        _gemm(q_in, w[f"{pre}.q{sfx}_w"], w[f"{pre}.q{sfx}_b"], out_bf16=qh)
+        _gemm(k_in, w[f"{pre}.k{sfx}_w"], w[f"{pre}.k{sfx}_b"], out_bf16=kh)
+        _gemm(v_in, w[f"{pre}.v{sfx}_w"], w[f"{pre}.v{sfx}_b"], out_bf16=vh)
+        o = ws.get(name + ".o" + sfx, (B * Tq, Cp), bf)
+        if flash:
+            ops.attn_flash(qh, 0, kh, 0, vh, 0, None, o, B, 8, Tq, Tk, 64, 1.0 / math.sqrt(hd))
+        else:
+            ops.attn_small(qh, kh, vh, o, B, 8, Tq, Tk, hd, 1.0 / math.sqrt(hd))
         self.launches += 4
-        return o
+        return o, w[f"{pre}.out{sfx}_w"]
 
     def transformer(self, feat: torch.Tensor, pe: torch.Tensor, tokens: torch.Tensor, B: int, Q: int):
         """TwoWayTransformer.forward (transformer.py:62-106) on token-major rows.
@@ -344,15 +366,15 @@ class DecoderEngine:
         for i in range(2):
             L = f"l{i}"
             if i == 0:  # skip_first_layer_pe: q = k = v = queries, output REPLACES the queries (transformer.py:155-156)
-                o = self._attention(L + ".self", Xb, Xb, Xb, B, Q, Q, "self")
-                _gemm(o, w[L + ".self.out_w"], w[L + ".self.out_b"], out_f32=Y)
+                o, ow = self._attention(L + ".self", Xb, Xb, Xb, B, Q, Q, "self")
+                _gemm(o, ow, w[L + ".self.out_b"], out_f32=Y)
             else:
-                o = self._attention(L + ".self", Xpe, Xpe, Xb, B, Q, Q, "self")
-                _gemm(o, w[L + ".self.out_w"], w[L + ".self.out_b"], X, MQ, out_f32=Y)
+                o, ow = self._attention(L + ".self", Xpe, Xpe, Xb, B, Q, Q, "self")
+                _gemm(o, ow, w[L + ".self.out_b"], X, MQ, out_f32=Y)
             ops.layernorm(Y, w[L + ".norm1_g"], w[L + ".norm1_b"], Xb, X, tokens, tmod, Xpe, 1e-5)
             # tokens -> image cross attention
-            o = self._attention(L + ".t2i", Xpe, keyspe, keysb, B, Q, NTOK, "t2i")
-            _gemm(o, w[L + ".t2i.out_w"], w[L + ".t2i.out_b"], X, MQ, out_f32=Y)
+            o, ow = self._attention(L + ".t2i", Xpe, keyspe, keysb, B, Q, NTOK, "t2i")
+            _gemm(o, ow, w[L + ".t2i.out_b"], X, MQ, out_f32=Y)
             ops.layernorm(Y, w[L + ".norm2_g"], w[L + ".norm2_b"], Xb, X, None, 0, None, 1e-5)
             # MLP
             hid = ws.get("hid", (MQ, 2048), bf)
@@ -360,14 +382,14 @@ class DecoderEngine:
             _gemm(hid, w[L + ".lin2_w"], w[L + ".lin2_b"], X, MQ, out_f32=Y)
             ops.layernorm(Y, w[L + ".norm3_g"], w[L + ".norm3_b"], Xb, X, tokens, tmod, Xpe, 1e-5)
             # image -> tokens cross attention (updates the keys)
-            o = self._attention(L + ".i2t", keyspe, Xpe, Xb, B, NTOK, Q, "i2t")
+            o, ow = self._attention(L + ".i2t", keyspe, Xpe, Xb, B, NTOK, Q, "i2t")
             ky = ws.get("keysY", (MK, 256), f32)
-            _gemm(o, w[L + ".i2t.out_w"], w[L + ".i2t.out_b"], keys_f32, MK, out_f32=ky)
+            _gemm(o, ow, w[L + ".i2t.out_b"], keys_f32, MK, out_f32=ky)
             ops.layernorm(ky, w[L + ".norm4_g"], w[L + ".norm4_b"], keysb, keys, pe, pmod, keyspe, 1e-5)
             keys_f32 = keys
             self.launches += 9
-        o = self._attention("final", Xpe, keyspe, keysb, B, Q, NTOK, "t2i")
-        _gemm(o, w["final.out_w"], w["final.out_b"], X, MQ, out_f32=Y)
+        o, ow = self._attention("final", Xpe, keyspe, keysb, B, Q, NTOK, "t2i")
+        _gemm(o, ow, w["final.out_b"], X, MQ, out_f32=Y)
         hs = ws.get("hs", (MQ, 256), f32)
         hsb = ws.get("hsb", (MQ, 256), bf)
         ops.layernorm(Y, w["nf_g"], w["nf_b"], hsb, hs, None, 0, None, 1e-5)

@@ -137,7 +137,7 @@ def run_reference(args):
                                    f"{args.batch})", "queries": args.queries},
             "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -346,13 +346,31 @@ def run_b200(args):
             "model_tflops": (value * gf / 1e3) if gf else None,
             "model_frac_of_bf16_peak": (value / world * gf / 1e3 / peaks["tflops"]) if gf else None,
             "breakdown_ms_per_step": {k: round(v["ms_per_step"], 3) for k, v in breakdown.items()}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Write the ONE JSON line to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # Libraries print to fd 1 behind Python's back (NCCL's version banner under torchrun): keep stdout for the JSON line only.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -139,6 +139,9 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const 
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the bulk stores committed so far have finished READING their shared-memory source
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent N committed groups
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_but() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // ------------------------------------------------------------------ CTA pairs (cluster of 2, tcgen05 cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -156,8 +159,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t rank) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_shared(smem_u32(local_bar), rank))
-               : "memory");
+  // default semantics (release at CTA scope): what is being ordered is tensor-memory traffic, which the tcgen05 fences
+  // around the barrier cover; `.release.cluster` costs a full memory barrier (ERRBAR) per arrive.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_shared(smem_u32(local_bar), rank)) : "memory");
 }
 // TMA load into this CTA's smem whose completion bytes are signalled on an mbarrier of the pair's leader CTA
 __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {

@@ -106,10 +106,12 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // more than half of the time -- profiles/r01c_gemm_shapes.jsonl, r01j_ncu_gemm_summary.txt.)
 // `tempty` is arrived on (once per warp) as soon as this warp has read its share of the accumulator; `remote` = the
 // barrier lives in the leader CTA of the pair (2-CTA kernel, non-leader CTA).
-template <int BN>
+// STAGE_BUFS = 4 KB staging buffers per warp (2 in the CTA-pair kernel): with two, single-output stores alternate between
+// them (`sbuf`, carried across tiles) and only wait for the store before the previous one.
+template <int BN, int STAGE_BUFS>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtensorMap* tc16, const CUtensorMap* tc32,
                                               uint8_t* stage, uint32_t tmem_acc, int tile_row0, int tile_n0, int warp,
-                                              int lane, uint64_t* tempty, bool remote) {
+                                              int lane, uint64_t* tempty, bool remote, uint32_t& sbuf) {
   const int q = warp & 3;                // TMEM lane quarter this warp may access
   const int half = (warp - 4) >> 2;      // column half of the tile
   constexpr int NCH = BN / 64;           // 32-column chunks per warp
@@ -137,14 +139,28 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
     const uint32_t st_row = smem_u32(stage) + (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
     const float* res_row = (p.residual != nullptr && !p.res_inplace) ? p.residual + (size_t)(row % p.res_mod) * p.ldr : nullptr;
+    const bool alt = STAGE_BUFS == 2 && p.tma_out == 1;  // single output: alternate the warp's two staging buffers
     uint32_t v[2][32];
+    float4 bq[2][8];  // bias of a chunk (the same 32 values in every lane), fetched one chunk ahead of its use
+    auto fetch_bias = [&](int c) {
+      const int n0 = tile_n0 + wcol0 + c * 32;
+      if (p.bias != nullptr && n0 + 32 <= p.N) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bq[c & 1][j] = __ldg(b4 + j);
+      }
+    };
     tmem_ld32(taddr, v[0]);
+    fetch_bias(0);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       if (c < nact) {
         const int n0 = tile_n0 + wcol0 + c * 32;
         tmem_ld_wait();  // chunk c has landed
-        if (c + 1 < NCH && c + 1 < nact) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+        if (c + 1 < NCH && c + 1 < nact) {
+          tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+          fetch_bias(c + 1);
+        }
         if (c == nact - 1) release();
         float f[32];
 #pragma unroll
@@ -152,11 +168,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         const bool full = n0 + 32 <= p.N;  // (N % 8 == 0 on this path; partial chunks only at the right edge)
         if (p.bias != nullptr) {
           if (full) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 bq = __ldg(b4 + j);
-              f[4 * j] += bq.x; f[4 * j + 1] += bq.y; f[4 * j + 2] += bq.z; f[4 * j + 3] += bq.w;
+              const float4 b = bq[c & 1][j];
+              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
             }
           } else {
 #pragma unroll
@@ -186,28 +201,37 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         }
         if (p.out_f32 != nullptr) {
           // ---- fp32 output: 32 columns = one 128-byte swizzled row per lane
-          if (lane == 0) tma_store_wait_read();  // the previous stores of this warp have finished reading the staging buffers
+          // the earlier stores of this warp have finished reading the staging buffer about to be rewritten
+          const uint32_t off32 = alt ? (sbuf & 1u) * 4096u : 0u;
+          if (lane == 0) {
+            if (alt) tma_store_wait_read_but<1>();
+            else tma_store_wait_read();
+          }
           __syncwarp();
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            sts128(st_row + ((k ^ sw) << 4), __float_as_uint(f[4 * k]), __float_as_uint(f[4 * k + 1]),
+            sts128(st_row + off32 + ((k ^ sw) << 4), __float_as_uint(f[4 * k]), __float_as_uint(f[4 * k + 1]),
                    __float_as_uint(f[4 * k + 2]), __float_as_uint(f[4 * k + 3]));
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (p.res_inplace) tma_reduce_add_2d(tc32, stage, n0, row0);
-            else tma_store_2d(tc32, stage, n0, row0);
+            if (p.res_inplace) tma_reduce_add_2d(tc32, stage + off32, n0, row0);
+            else tma_store_2d(tc32, stage + off32, n0, row0);
             tma_store_commit();
           }
+          ++sbuf;
         }
         if (p.out_bf16 != nullptr) {
           // ---- bf16 output: two chunks share one 128-byte row (64 columns): even chunk -> 16-byte pieces 0..3, odd -> 4..7.
           // An unpaired last chunk only happens at the right edge of the matrix, where TMA clips the unwritten half.
           // With both outputs (tma_out == 2, CTA-pair kernel) the bf16 rows use the warp's second staging buffer; the
           // wait above (every chunk) already covers its reuse.
-          const uint32_t off16 = (p.out_f32 != nullptr) ? 4096u : 0u;
+          const uint32_t off16 = (p.out_f32 != nullptr) ? 4096u : (alt ? (sbuf & 1u) * 4096u : 0u);
           if ((c & 1) == 0 && p.out_f32 == nullptr) {
-            if (lane == 0) tma_store_wait_read();
+            if (lane == 0) {
+              if (alt) tma_store_wait_read_but<1>();
+              else tma_store_wait_read();
+            }
             __syncwarp();
           }
 #pragma unroll
@@ -222,6 +246,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
               tma_store_2d(tc16, stage + off16, n0 - (c & 1) * 32, row0);
               tma_store_commit();
             }
+            if (p.out_f32 == nullptr) ++sbuf;
           }
         }
       }
@@ -396,13 +421,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------ epilogue (8 warps; see epilogue_tile)
     uint8_t* stage_buf = smem + Cfg::OFF_EPI + (warp - 4) * 4096;
     int as = 0;
-    uint32_t aphase = 0;
+    uint32_t aphase = 0, sbuf = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_blk = t % num_n, m_blk = t / num_n;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN>(p, &tmap_c16, &tmap_c32, stage_buf, tmem_base + as * BN, m_blk * BM, n_blk * BN, warp, lane,
-                        &tempty_bar[as], false);
+      epilogue_tile<BN, 1>(p, &tmap_c16, &tmap_c32, stage_buf, tmem_base + as * BN, m_blk * BM, n_blk * BN, warp, lane,
+                           &tempty_bar[as], false, sbuf);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (lane == 0) tma_store_wait_read();  // the staging buffer must stay valid until the last store has read it
@@ -541,13 +566,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ------------------------------------------------------------ epilogue (both CTAs: own 128 rows of the tile)
     uint8_t* stage_buf = smem + Cfg::OFF_EPI + (warp - 4) * 8192;
     int as = 0;
-    uint32_t aphase = 0;
+    uint32_t aphase = 0, sbuf = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       const int n_blk = t % num_n, m_blk = t / num_n;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN>(p, &tmap_c16, &tmap_c32, stage_buf, tmem_base + as * BN, m_blk * 256 + (int)rank * 128, n_blk * BN,
-                        warp, lane, &tempty_bar[as], rank != 0);
+      epilogue_tile<BN, 2>(p, &tmap_c16, &tmap_c32, stage_buf, tmem_base + as * BN, m_blk * 256 + (int)rank * 128, n_blk * BN,
+                           warp, lane, &tempty_bar[as], rank != 0, sbuf);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (lane == 0) tma_store_wait_read();

@@ -143,6 +143,30 @@ int wm_nms(const float* boxes, const float* scores, const int64_t* labels, int n
 int wm_nms_batched(const float* packed, const int32_t* counts, int B, int Q, float score_thr, double iou_thr,
                    int per_class, int32_t* keep_idx, int32_t* keep_cnt, void* stream);
 
+/* ---- either side of the path: uint8 tile front-end, image-level merge, COCO packing ---- */
+
+/* Tiles cut out of ONE uint8 HWC survey image (device memory, `row_stride` bytes between rows) at origins int32 [T,2] =
+ * (y0, x0) (device): out fp32 [T,3,1024,1024] = ((u8 / 255) - mean[c]) / std[c] for the first content_h x content_w
+ * pixels of each tile that lie inside the image, 0 elsewhere.  Replaces torchvision to_tensor + normalize
+ * (dataloader_coco.py:286-292, utils/augmentation.py:229-249) and the zero padding of nested_tensor_from_tensor_list
+ * (utils/misc.py:46-67); bit-exact (IEEE division, same operation order).  mean/std: host pointers to 3 floats. */
+int wm_tiles_from_u8(const uint8_t* img, int H, int W, int64_t row_stride, const int32_t* origins, int T, int content_h,
+                     int content_w, const float* mean3, const float* std3, float* out, void* stream);
+
+/* Image-level candidate list from the packed per-tile PostProcess rows (packed fp32 [T,Q,6], counts int32 [T], Q <= 1024):
+ * rows with score > score_thr (visualize_prediction.py:150) in tile-major, query order; boxes moved by the tile origin
+ * (fp32 add of (x0, y0)).  tile_n_ws int32 [T]; outputs boxes fp32 [T*Q,4], scores fp32 [T*Q], labels int64 [T*Q],
+ * src int32 [T*Q,2] = (tile, row), total int32 [1].  Feed the first `total` entries to wm_nms (labels => per class). */
+int wm_merge_detections(const float* packed, const int32_t* counts, const int32_t* origins, int T, int Q, float score_thr,
+                        int32_t* tile_n_ws, float* boxes, float* scores, int64_t* labels, int32_t* src, int32_t* total,
+                        void* stream);
+
+/* COCO detection records for the kept detections (inference.py:149-171, convert_to_xywh :235-237):
+ * out_xywh_score fp32 [n_keep,5] = (x, y, x1 - x0, y1 - y0, score), out_category int64 [n_keep]; keep int64 [n_keep]
+ * indexes boxes/scores/labels (NULL = identity). */
+int wm_pack_coco(const float* boxes, const float* scores, const int64_t* labels, const int64_t* keep, int n_keep,
+                 float* out_xywh_score, int64_t* out_category, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

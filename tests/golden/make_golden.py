@@ -11,6 +11,8 @@ PostProcess / torchvision NMS on seeded inputs and stores small fixtures:
   golden_model_<cfg>.npz  logits, boxes, and per-stage samples (fixed pseudo-random positions)
   golden_post.npz         PostProcess outputs for seeded logits/boxes
   golden_nms.npz          torchvision.ops.nms keep lists (class-agnostic and per-class)
+  golden_frontend.npz     ToTensor + Normalize + nested_tensor_from_tensor_list on seeded uint8 crops (hash + samples),
+                          convert_to_xywh on seeded boxes
 """
 from __future__ import annotations
 
@@ -27,6 +29,7 @@ sys.path.insert(0, ROOT)
 REF = "/root/reference/wildlifemapper"
 
 from oracle import post as opost  # noqa: E402
+from oracle.frontend import FRONTEND_CASES, frontend_image  # noqa: E402
 from oracle.weights import MODEL_CONFIGS, make_state_dict, make_tiles  # noqa: E402
 
 N_SAMPLES = 256
@@ -160,9 +163,45 @@ def golden_nms() -> None:
     print("wrote golden_nms", {k: (v.shape if hasattr(v, "shape") else v) for k, v in res.items()})
 
 
+def golden_frontend() -> None:
+    import hashlib
+    import re
+    from PIL import Image
+    sys.path.insert(0, REF)
+    import segment_anything.utils.augmentation as T
+    from segment_anything.utils.misc import nested_tensor_from_tensor_list
+    norm = T.Compose([T.ToTensor(), T.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])  # dataloader_coco.py:286-290
+    res = {}
+    for tag, hw, (y0, x0), (ch, cw) in FRONTEND_CASES:
+        img = frontend_image(tag, hw)
+        crop = np.ascontiguousarray(img[y0:y0 + ch, x0:x0 + cw])  # the tile file the reference's loader would open
+        t, _ = norm(Image.fromarray(crop), None)
+        nt = nested_tensor_from_tensor_list([t])
+        out = nt.tensors[0].numpy()
+        assert out.shape == (3, 1024, 1024)
+        res[f"{tag}.sha256"] = np.array(hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest())
+        res[f"{tag}.samples"] = out.reshape(-1)[sample_positions(out.size, tag)]
+        res[f"{tag}.sum"] = np.array([np.abs(out.astype(np.float64)).sum()])
+    # convert_to_xywh lives in inference.py, which does not import here (pycocotools): run its source text
+    src = open(os.path.join(REF, "inference.py")).read()
+    m = re.search(r"^def convert_to_xywh\(boxes\):\n(?:[ \t]+.*\n)+", src, re.M)
+    ns = {"torch": torch}
+    exec(m.group(0), ns)
+    g = torch.Generator().manual_seed(5)
+    xy = torch.rand(64, 2, generator=g) * 5000
+    wh = torch.rand(64, 2, generator=g) * 60 + 1
+    boxes = torch.cat([xy, xy + wh], 1)
+    res["xywh.boxes"] = boxes.numpy()
+    res["xywh.out"] = ns["convert_to_xywh"](boxes).numpy()
+    np.savez_compressed(os.path.join(HERE, "golden_frontend.npz"), **res)
+    print("wrote golden_frontend", {k: (v.shape if v.ndim else str(v)[:16]) for k, v in res.items()})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 8)
-    which = sys.argv[1:] or ["post", "nms", "vit_t", "vit_t900", "vit_b"]
+    which = sys.argv[1:] or ["post", "nms", "frontend", "vit_t", "vit_t900", "vit_b"]
+    if "frontend" in which:
+        golden_frontend()
     if "post" in which:
         golden_post()
     if "nms" in which:

@@ -154,3 +154,24 @@ def test_gather_detections_gloo_world2():
         p.join(60)
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] and r[2] and r[3] for r in res)
+
+
+def test_plan_tiles_covers_image_with_overlap():
+    """Host logic of the survey front-end (wildlifemapper_b200/survey.py): every pixel is covered, neighbours share at
+    least `overlap` pixels, no tile hangs over the border unless the image is smaller than a tile."""
+    from wildlifemapper_b200.survey import plan_tiles
+    for H, W, tile, ov in [(3648, 5472, 1024, 128), (1024, 1024, 1024, 128), (700, 2000, 1024, 0), (1025, 1024, 1024, 512),
+                           (4000, 3000, 768, 64)]:
+        org = plan_tiles(H, W, tile, ov)
+        cover = np.zeros((H, W), bool)
+        for y, x in org:
+            assert y >= 0 and x >= 0 and (y + tile <= H or H <= tile) and (x + tile <= W or W <= tile)
+            cover[y:y + tile, x:x + tile] = True
+        assert cover.all() and len(set(org)) == len(org)
+        ys, xs = sorted({y for y, _ in org}), sorted({x for _, x in org})
+        assert all(b - a <= tile - ov for a, b in zip(ys, ys[1:])) and all(b - a <= tile - ov for a, b in zip(xs, xs[1:]))
+    assert plan_tiles(3648, 5472)[-1] == (3648 - 1024, 5472 - 1024) and len(plan_tiles(3648, 5472)) == 24
+    with pytest.raises(ValueError):
+        plan_tiles(0, 10)
+    with pytest.raises(ValueError):
+        plan_tiles(10, 10, 1024, 1024)

@@ -23,6 +23,11 @@ int sigmoid_topk_launch(const float*, const float*, float*, int*, float*, int*, 
 int nms_launch(const float*, const float*, const long long*, int, double, int*, unsigned long long*, long long*, int*,
                cudaStream_t);
 int nms_batched_small_launch(const float*, const int*, int, int, float, double, int, int*, int*, cudaStream_t);
+int tiles_from_u8_launch(const uint8_t*, int, int, long long, const int*, int, int, int, const float*, const float*, float*,
+                         cudaStream_t);
+int merge_detections_launch(const float*, const int*, const int*, int, int, float, int*, float*, float*, long long*, int*,
+                            int*, cudaStream_t);
+int coco_pack_launch(const float*, const float*, const long long*, const long long*, int, float*, long long*, cudaStream_t);
 }  // namespace wm
 
 namespace {
@@ -411,6 +416,42 @@ int wm_nms_batched(const float* packed, const int32_t* counts, int B, int Q, flo
   return check_launch(wm::nms_batched_small_launch(packed, counts, B, Q, score_thr, iou_thr, per_class, keep_idx, keep_cnt,
                                                    (cudaStream_t)stream),
                       "wm_nms_batched");
+}
+
+int wm_tiles_from_u8(const uint8_t* img, int H, int W, int64_t row_stride, const int32_t* origins, int T, int content_h,
+                     int content_w, const float* mean3, const float* std3, float* out, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (H <= 0 || W <= 0 || T < 0 || row_stride < (int64_t)W * 3 || content_h < 0 || content_h > 1024 || content_w < 0 ||
+      content_w > 1024)
+    return fail(WM_ERR_SHAPE, "wm_tiles_from_u8: bad shape H=%d W=%d T=%d stride=%lld content=%dx%d", H, W, T,
+                (long long)row_stride, content_h, content_w);
+  if (mean3 == nullptr || std3 == nullptr || (T > 0 && (img == nullptr || origins == nullptr || out == nullptr)))
+    return fail(WM_ERR_SHAPE, "wm_tiles_from_u8: null pointer");
+  if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return fail(WM_ERR_ALIGN, "wm_tiles_from_u8: out must be 16-byte aligned");
+  return check_launch(wm::tiles_from_u8_launch(img, H, W, row_stride, origins, T, content_h, content_w, mean3, std3, out,
+                                               (cudaStream_t)stream),
+                      "wm_tiles_from_u8");
+}
+
+int wm_merge_detections(const float* packed, const int32_t* counts, const int32_t* origins, int T, int Q, float score_thr,
+                        int32_t* tile_n_ws, float* boxes, float* scores, int64_t* labels, int32_t* src, int32_t* total,
+                        void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (T < 0 || Q <= 0 || Q > 1024) return fail(WM_ERR_SHAPE, "wm_merge_detections: needs T >= 0 and 0 < Q <= 1024");
+  if (total == nullptr) return fail(WM_ERR_SHAPE, "wm_merge_detections: null pointer");
+  return check_launch(wm::merge_detections_launch(packed, counts, origins, T, Q, score_thr, tile_n_ws, boxes, scores,
+                                                  reinterpret_cast<long long*>(labels), src, total, (cudaStream_t)stream),
+                      "wm_merge_detections");
+}
+
+int wm_pack_coco(const float* boxes, const float* scores, const int64_t* labels, const int64_t* keep, int n_keep,
+                 float* out_xywh_score, int64_t* out_category, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (n_keep < 0) return fail(WM_ERR_SHAPE, "wm_pack_coco: n_keep < 0");
+  return check_launch(wm::coco_pack_launch(boxes, scores, reinterpret_cast<const long long*>(labels),
+                                           reinterpret_cast<const long long*>(keep), n_keep, out_xywh_score,
+                                           reinterpret_cast<long long*>(out_category), (cudaStream_t)stream),
+                      "wm_pack_coco");
 }
 
 }  // extern "C"

@@ -38,6 +38,9 @@ SIGNATURES = {
     "wm_sigmoid_topk": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "wm_nms": [_p, _p, _p, _i, _d, _p, _p, _p, _p, _p],
     "wm_nms_batched": [_p, _p, _i, _i, _f, _d, _i, _p, _p, _p],
+    "wm_tiles_from_u8": [_p, _i, _i, _i64, _p, _i, _i, _i, _p, _p, _p, _p],
+    "wm_merge_detections": [_p, _p, _p, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p],
+    "wm_pack_coco": [_p, _p, _p, _p, _i, _p, _p, _p],
 }
 
 _lib = None

@@ -241,4 +241,57 @@ def _nms_batched(packed, counts, score_thr, iou_thr, per_class, keep_idx, keep_c
 _define("nms_batched(Tensor packed, Tensor counts, float score_thr, float iou_thr, int per_class, "
         "Tensor(a!) keep_idx, Tensor(b!) keep_cnt) -> ()", _nms_batched)
 
+# ------------------------------------------------------------------ tile front-end / merge / COCO packing (section 8f)
+def _tiles_from_u8(img, origins, content_h, content_w, mean, std, out):
+    _chk(img, torch.uint8, "tiles_from_u8.img"); _chk(origins, torch.int32, "tiles_from_u8.origins")
+    _chk(out, torch.float32, "tiles_from_u8.out")
+    H, W, three = img.shape
+    T = origins.shape[0]
+    assert three == 3 and img.stride(1) == 3 and origins.is_contiguous() and out.is_contiguous()
+    assert tuple(out.shape) == (T, 3, 1024, 1024) and len(mean) == 3 and len(std) == 3
+    import ctypes as C
+    # fp32 mean / std exactly as torch.as_tensor(mean, dtype=float32) rounds them (torchvision normalize)
+    m = (C.c_float * 3)(*[float(x) for x in mean]); sd = (C.c_float * 3)(*[float(x) for x in std])
+    _lib.call("wm_tiles_from_u8", img.data_ptr(), H, W, img.stride(0), origins.data_ptr(), T, int(content_h), int(content_w),
+              C.addressof(m), C.addressof(sd), out.data_ptr(), _stream())
+
+
+_define("tiles_from_u8(Tensor img, Tensor origins, int content_h, int content_w, float[] mean, float[] std, "
+        "Tensor(a!) out) -> ()", _tiles_from_u8)
+
+
+def _merge_detections(packed, counts, origins, score_thr, tile_n_ws, boxes, scores, labels, src, total):
+    _chk(packed, torch.float32, "merge_detections.packed"); _chk(counts, torch.int32, "merge_detections.counts")
+    _chk(origins, torch.int32, "merge_detections.origins"); _chk(tile_n_ws, torch.int32, "merge_detections.tile_n_ws")
+    _chk(boxes, torch.float32, "merge_detections.boxes"); _chk(scores, torch.float32, "merge_detections.scores")
+    _chk(labels, torch.int64, "merge_detections.labels"); _chk(src, torch.int32, "merge_detections.src")
+    _chk(total, torch.int32, "merge_detections.total")
+    T, Q, six = packed.shape
+    assert six == 6 and packed.is_contiguous() and counts.numel() == T and origins.numel() == 2 * T
+    assert boxes.numel() >= 4 * T * Q and scores.numel() >= T * Q and labels.numel() >= T * Q and src.numel() >= 2 * T * Q
+    assert tile_n_ws.numel() >= T
+    _lib.call("wm_merge_detections", packed.data_ptr(), counts.data_ptr(), origins.data_ptr(), T, Q, float(score_thr),
+              tile_n_ws.data_ptr(), boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), src.data_ptr(),
+              total.data_ptr(), _stream())
+
+
+_define("merge_detections(Tensor packed, Tensor counts, Tensor origins, float score_thr, Tensor(a!) tile_n_ws, "
+        "Tensor(b!) boxes, Tensor(c!) scores, Tensor(d!) labels, Tensor(e!) src, Tensor(f!) total) -> ()",
+        _merge_detections)
+
+
+def _pack_coco(boxes, scores, labels, keep, n_keep, out_xywh_score, out_category):
+    _chk(boxes, torch.float32, "pack_coco.boxes"); _chk(scores, torch.float32, "pack_coco.scores")
+    _chk(labels, torch.int64, "pack_coco.labels"); _chk(keep, torch.int64, "pack_coco.keep")
+    _chk(out_xywh_score, torch.float32, "pack_coco.out"); _chk(out_category, torch.int64, "pack_coco.out_category")
+    assert boxes.is_contiguous() and out_xywh_score.is_contiguous()
+    assert out_xywh_score.numel() >= 5 * n_keep and out_category.numel() >= n_keep
+    assert keep is None or keep.numel() >= n_keep
+    _lib.call("wm_pack_coco", boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), _ptr(keep), int(n_keep),
+              out_xywh_score.data_ptr(), out_category.data_ptr(), _stream())
+
+
+_define("pack_coco(Tensor boxes, Tensor scores, Tensor labels, Tensor? keep, int n_keep, Tensor(a!) out_xywh_score, "
+        "Tensor(b!) out_category) -> ()", _pack_coco)
+
 ops = torch.ops.wm_b200

@@ -166,7 +166,7 @@ def image_encoder(sd: Dict[str, Tensor], model_type: str, img: Tensor, x_hfc: Te
 # --------------------------------------------------------------------------- decoder
 def dense_pe(G: Tensor, size: int = GRID) -> Tensor:
     """PromptEncoder.get_dense_pe; pos_encoder.py:24-33,50-70. Returns [1,256,size,size]."""
-    g = (torch.arange(size, dtype=torch.float32) + 0.5) / size
+    g = (torch.arange(size, dtype=torch.float32, device=G.device) + 0.5) / size
     xy = torch.stack([g[None, :].expand(size, size), g[:, None].expand(size, size)], dim=-1)  # (x, y)
     c = 2 * math.pi * ((2 * xy - 1) @ G)
     return torch.cat([torch.sin(c), torch.cos(c)], dim=-1).permute(2, 0, 1).unsqueeze(0)

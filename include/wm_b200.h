@@ -51,6 +51,8 @@ int wm_set_option(const char* name, int value);
 /* Diagnostics build only (csrc/build.sh with -DWM_F3_TRACE): copy the SM-clock event trace of CTA (0,0,0) of the last
  * v3 / v4 flash-attention launch (whichever generation is selected) to host_out[3][64][8]; WM_ERR_ARCH in the product build. */
 int wm_debug_flash_trace(uint64_t* host_out_3x64x4);
+/* Same for CTA 0 of the last windowed-attention (v2) launch: host_out[3][64][8]. */
+int wm_debug_window_trace(uint64_t* host_out_3x64x8);
 
 /* C[M,N] = act(A[M,K] * W[N,K]^T + bias) + residual[(m % res_mod), :]      (tcgen05 / TMEM / TMA)
  * Replaces every nn.Linear / 1x1 Conv2d / patch-embed Conv2d(k16,s16) on the path:

@@ -325,6 +325,12 @@ int wm_debug_flash_trace(uint64_t* host_out_3x64x4) {
   return WM_OK;
 }
 
+int wm_debug_window_trace(uint64_t* host_out_3x64x8) {
+  if (wm::window2_read_trace(reinterpret_cast<unsigned long long*>(host_out_3x64x8)) != WM_OK)
+    return fail(WM_ERR_ARCH, "wm_debug_window_trace: only available in the diagnostics build (-DWM_F3_TRACE)");
+  return WM_OK;
+}
+
 int wm_attn_window(const void* qkv, const void* rel_table, void* out_bf16, int B, int H, int D, float scale,
                    void* stream) {
   if (int rc = ensure_device()) return rc;

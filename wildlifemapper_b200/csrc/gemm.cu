@@ -46,45 +46,54 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN >= 32 ? 2 * BN : 32;
 };
 
-// Exact-erf GELU (nn.GELU(), M/common.py:13-26): 0.5 x (1 + erf(x / sqrt 2)), with erf(z) = z P(z^2) for |z| <= 3
-// (degree-8 minimax fit, |error| <= 1.7e-5; saturated beyond: 1 - erf(3) = 2.2e-5).  15 FMA/ALU-pipe operations and
-// no MUFU: the GELU epilogue has to stay under the main-loop time of the next tile (erff() costs ~25 operations, a
-// rcp/ex2 formulation 2 MUFU per element -- both measured slower, profiles/r01i_gemm_shapes.jsonl).  The resulting
-// |error| <= 6.2e-5 on GELU is far below the bf16 rounding of the stored activation.
+// Exact-erf GELU (nn.GELU(), M/common.py:13-26): x (0.5 + 0.5 erf(x / sqrt 2)) = x (0.5 + xc Q(xc^2)) with
+// xc = clamp(x, +-3 sqrt 2) and Q a degree-8 fit of 0.5 erf(x / sqrt 2) / x in x^2 (saturated beyond: 1 - erf(3) = 2.2e-5).
+// 11 FMA-pipe operations and no MUFU: the GELU epilogue has to stay under the main-loop time of the next tile (erff()
+// costs ~25 operations, a rcp/ex2 formulation 2 MUFU per element -- both measured slower; the packed fp32x2 forms issue
+// at half rate, so the operation count is what matters -- profiles/r01z_ncu_gemm_gelu_summary.txt).  |error| <= 6.3e-5
+// on GELU, far below the bf16 rounding of the stored activation.
+#define WM_GELU_C0 0.3988664448261261f
+#define WM_GELU_C1 -0.06624268740415573f
+#define WM_GELU_C2 0.00973955076187849f
+#define WM_GELU_C3 -0.0010831074323505163f
+#define WM_GELU_C4 8.891491597751155e-05f
+#define WM_GELU_C5 -5.17239732289454e-06f
+#define WM_GELU_C6 1.99358936470162e-07f
+#define WM_GELU_C7 -4.523354135699265e-09f
+#define WM_GELU_C8 4.543853834859668e-11f
+#define WM_GELU_LIM 4.242640687119285f
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fminf(fmaxf(x * 0.70710678118654752f, -3.0f), 3.0f);
-  const float z2 = z * z;
-  float pl = fmaf(4.074191295444507e-08f, z2, -1.944815949173062e-06f);
-  pl = fmaf(pl, z2, 4.106042979401536e-05f);
-  pl = fmaf(pl, z2, -0.0005110361380502582f);
-  pl = fmaf(pl, z2, 0.004235424567013979f);
-  pl = fmaf(pl, z2, -0.025102855637669563f);
-  pl = fmaf(pl, z2, 0.11107932776212692f);
-  pl = fmaf(pl, z2, -0.375314861536026f);
-  pl = fmaf(pl, z2, 1.1282684803009033f);
-  const float hx = 0.5f * x;
-  return fmaf(hx, pl * z, hx);
+  const float xc = fminf(fmaxf(x, -WM_GELU_LIM), WM_GELU_LIM);
+  const float t = xc * xc;
+  float q = fmaf(WM_GELU_C8, t, WM_GELU_C7);
+  q = fmaf(q, t, WM_GELU_C6);
+  q = fmaf(q, t, WM_GELU_C5);
+  q = fmaf(q, t, WM_GELU_C4);
+  q = fmaf(q, t, WM_GELU_C3);
+  q = fmaf(q, t, WM_GELU_C2);
+  q = fmaf(q, t, WM_GELU_C1);
+  q = fmaf(q, t, WM_GELU_C0);
+  return x * fmaf(xc, q, 0.5f);
 }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// Two GELUs at once on the packed fp32x2 FMA path of sm_100 (FFMA2 / FMUL2: one issue slot per pair; common.cuh)
+// Two GELUs at once on the packed fp32x2 FMA path of sm_100 (FFMA2 / FMUL2; common.cuh)
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
-  const float z0 = fminf(fmaxf(x0 * 0.70710678118654752f, -3.0f), 3.0f);
-  const float z1 = fminf(fmaxf(x1 * 0.70710678118654752f, -3.0f), 3.0f);
-  const uint64_t z = pk2(z0, z1);
-  const uint64_t z2 = mul2(z, z);
-  uint64_t pl = fma2(pk2(4.074191295444507e-08f, 4.074191295444507e-08f), z2, pk2(-1.944815949173062e-06f, -1.944815949173062e-06f));
-  pl = fma2(pl, z2, pk2(4.106042979401536e-05f, 4.106042979401536e-05f));
-  pl = fma2(pl, z2, pk2(-0.0005110361380502582f, -0.0005110361380502582f));
-  pl = fma2(pl, z2, pk2(0.004235424567013979f, 0.004235424567013979f));
-  pl = fma2(pl, z2, pk2(-0.025102855637669563f, -0.025102855637669563f));
-  pl = fma2(pl, z2, pk2(0.11107932776212692f, 0.11107932776212692f));
-  pl = fma2(pl, z2, pk2(-0.375314861536026f, -0.375314861536026f));
-  pl = fma2(pl, z2, pk2(1.1282684803009033f, 1.1282684803009033f));
-  const uint64_t hx = mul2(pk2(x0, x1), pk2(0.5f, 0.5f));
-  const uint64_t r = fma2(hx, mul2(pl, z), hx);
+  const float c0 = fminf(fmaxf(x0, -WM_GELU_LIM), WM_GELU_LIM);
+  const float c1 = fminf(fmaxf(x1, -WM_GELU_LIM), WM_GELU_LIM);
+  const uint64_t xc = pk2(c0, c1);
+  const uint64_t t = mul2(xc, xc);
+  uint64_t q = fma2(pk2(WM_GELU_C8, WM_GELU_C8), t, pk2(WM_GELU_C7, WM_GELU_C7));
+  q = fma2(q, t, pk2(WM_GELU_C6, WM_GELU_C6));
+  q = fma2(q, t, pk2(WM_GELU_C5, WM_GELU_C5));
+  q = fma2(q, t, pk2(WM_GELU_C4, WM_GELU_C4));
+  q = fma2(q, t, pk2(WM_GELU_C3, WM_GELU_C3));
+  q = fma2(q, t, pk2(WM_GELU_C2, WM_GELU_C2));
+  q = fma2(q, t, pk2(WM_GELU_C1, WM_GELU_C1));
+  q = fma2(q, t, pk2(WM_GELU_C0, WM_GELU_C0));
+  const uint64_t r = mul2(pk2(x0, x1), fma2(xc, q, pk2(0.5f, 0.5f)));
   unpk2(r, x0, x1);
 }
 

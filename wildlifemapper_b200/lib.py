@@ -23,6 +23,7 @@ SIGNATURES = {
     "wm_set_flash_version": [_i],
     "wm_set_option": [C.c_char_p, _i],
     "wm_debug_flash_trace": [_p],
+    "wm_debug_window_trace": [_p],
     "wm_gemm_bf16": [_p, _i64, _p, _i64, _p, _p, _i64, _i, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _p],
     "wm_conv3x3_nhwc_bf16": [_p, _p, _p, _p, _i, _i, _i, _p],
     "wm_layernorm": [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _f, _p],

@@ -84,7 +84,7 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint64_t* v_empty = bars + 13;  // [4]
   uint64_t* s_full = bars + 17;   // [2 tiles][2 buffers]  S_t(j) complete
   uint64_t* p_full = bars + 21;   // [2 tiles][2 buffers]  P_t(j) stored to TMEM by the 4 warps of tile t
-  uint64_t* pv_done = bars + 25;  // [2]  P_t(j) V complete (only waited on by the rare rescale path)
+  uint64_t* pv_done = bars + 25;  // [2]  P_t(ns-2) V, P_t(ns-1) V complete (only waited on by the rare rescale path)
   uint64_t* o_full = bars + 27;   // [2]
   uint64_t* t_full = bars + 29;   // rel-pos table products complete
   uint64_t* t_done = bars + 30;   // ... and drained out of the S / O columns by the 8 softmax warps
@@ -105,9 +105,9 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     mbar_init(q_full, 1);
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], 2);  // released by both MMA warps
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], 2);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
@@ -131,6 +131,79 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     setmaxnreg_dec<40>();
     // Producer and MMA roles: the WHOLE warp runs the control flow (uniform branches, every lane polls the
     // barriers); one elected lane issues the TMA / tcgen05 instructions.
+    // Main loop of one MMA issuer warp for query tile t (warp 1: tile 0, warp 3: tile 1).  One issuer per tile: a single
+    // warp walking both tiles spent ~2000 of the 2700 cycles of a 64-key step in its own control flow -- every mbarrier
+    // wait costs ~100 cycles even when the phase has long completed, every tcgen05.mma / commit is issued by one lane
+    // that shares its scheduler with two softmax warps -- and saw each tile's P 3000 cycles after it had been stored,
+    // while the tensor pipe needs 52 cycles per 128 x 64 x 16 MMA (profiles/r01z_flash4_trace_before.txt,
+    // profiles/micro/umma_chain_bench.cu).
+    auto mma_main = [&](const int t, const bool leader) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);  // A = P from TMEM (K-major), V is MN-major
+      const uint32_t sq = smem_u32(smem + Cfg::OFF_Q);
+      // S_t(step) = Q_t K(step)^T (128 x 64 x HD) into score buffer (step & 1) of tile t; K rows of step: half (step & 1)
+      // of stage (step / 2) % NS.
+      auto issue_s = [&](int step) {
+        if (leader) {
+          const int kst = (step >> 1) % NS;
+          const uint64_t qd = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES, 16, 1024);
+          const uint64_t kd = make_sdesc_sw128(smem_u32(smem + Cfg::OFF_K + kst * Cfg::TILE_BYTES) + (step & 1) * 8192, 16, 1024);
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+            const uint32_t off = (uint32_t)((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);  // address field is bytes >> 4
+            umma_bf16(tmem_base + t * 128 + (step & 1) * 64, qd + off, kd + off, idesc_s, ks != 0);
+          }
+          umma_commit(&s_full[t * 2 + (step & 1)]);
+        }
+        __syncwarp();
+      };
+      // two steps ahead of the softmax (both from K tile 0)
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      issue_s(1);
+      if (leader) umma_commit(&k_empty[0]);
+      __syncwarp();
+      for (int j = 0; j < ns; ++j) {
+        const int vst = (j >> 1) % NS;
+        const uint32_t vph = (uint32_t)((j >> 1) / NS) & 1u;
+        const bool more = j + 2 < ns;
+        const uint32_t sv = smem_u32(smem + Cfg::OFF_V + vst * Cfg::TILE_BYTES) + (j & 1) * 8192;
+        if (leader) F4_TRACE(2, j, 4 * t);
+        mbar_wait(&p_full[t * 2 + (j & 1)], (uint32_t)(j >> 1) & 1u);
+        if (leader) F4_TRACE(2, j, 4 * t + 1);
+        if ((j & 1) == 0) {
+          mbar_wait(&v_full[vst], vph);
+          if (more) {  // step j + 2 opens K tile (j + 2) / 2
+            const int kt = (j + 2) >> 1;
+            mbar_wait(&k_full[kt % NS], (uint32_t)(kt / NS) & 1u);
+          }
+        }
+        tc_fence_after();
+        if (leader) {
+          const uint64_t vd = make_sdesc_sw128(sv, 16384, 1024);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)  // 64 keys, 16 per MMA; P: 8 TMEM columns per step; V: 2048 B per step
+            umma_bf16_ts(tmem_base + Cfg::COL_O + t * HD, tmem_base + t * 128 + (j & 1) * 64 + ks * 8,
+                         vd + (uint32_t)(ks * (2048 >> 4)), idesc_pv, (j | ks) != 0);
+          // P_t(j) V complete: only the rare rescale path of step j + 1 needs it; while score tiles are still being
+          // issued behind the P V groups, the commit of S_t(j + 2) covers it (the pipe completes in issue order), so the
+          // explicit commit (~44 cycles of tensor-pipe issue time, profiles/micro/umma_chain_bench.cu) is only paid by the
+          // last two steps.
+          if (!more) umma_commit(&pv_done[t]);
+          if (j == ns - 1) umma_commit(&o_full[t]);
+        }
+        __syncwarp();
+        if (leader) F4_TRACE(2, j, 4 * t + 2);
+        if (more) issue_s(j + 2);  // reuses the score buffer step j just released (behind its P V in the pipe)
+        if (leader) F4_TRACE(2, j, 4 * t + 3);
+        if (leader) {
+          if (j & 1) umma_commit(&v_empty[vst]);                            // both halves of the V tile consumed by this tile
+          if (more && (j & 1)) umma_commit(&k_empty[((j + 2) >> 1) % NS]);  // both halves of K tile (j + 2) / 2 issued
+        }
+        __syncwarp();
+      }
+    };
     if (warp == 0) {
       // ------------------------------------------------------------ TMA producer
       if (elect_one()) {
@@ -180,8 +253,6 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       }
     } else if (warp == 1) {
       // ------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);  // A = P from TMEM (K-major), V is MN-major
       const bool leader = elect_one();  // the same lane issues every tcgen05.mma / tcgen05.commit
       const uint32_t sq = smem_u32(smem + Cfg::OFF_Q);
       mbar_wait(q_full, 0);
@@ -216,71 +287,14 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         mbar_wait(t_done, 0);  // both warpgroups have drained the scratch out of the S / O columns
         tc_fence_after();
       }
-      // S_t(step) = Q_t K(step)^T (128 x 64 x HD) into score buffer (step & 1) of tile t; K rows of step: half (step & 1)
-      // of stage (step / 2) % NS.  (MMAs that accumulate into the same tensor-memory tile are serialised by the
-      // accumulator round trip, ~90 cycles per 128 x 64 x 16 step; issuing the two tiles' chains interleaved shortens
-      // the issue time but forces the tiles into lockstep and measured slower end to end: profiles/r01u_flash4_*.txt.)
-      auto issue_s = [&](int t, int step) {
-        if (leader) {
-          const int kst = (step >> 1) % NS;
-          const uint64_t qd = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES, 16, 1024);
-          const uint64_t kd = make_sdesc_sw128(smem_u32(smem + Cfg::OFF_K + kst * Cfg::TILE_BYTES) + (step & 1) * 8192, 16, 1024);
-#pragma unroll
-          for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
-            const uint32_t off = (uint32_t)((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);  // address field is bytes >> 4
-            umma_bf16(tmem_base + t * 128 + (step & 1) * 64, qd + off, kd + off, idesc_s, ks != 0);
-          }
-          umma_commit(&s_full[t * 2 + (step & 1)]);
-        }
-        __syncwarp();
-      };
-      // two steps ahead of the softmax (both from K tile 0)
-      mbar_wait(&k_full[0], 0);
+      mma_main(0, leader);
+    } else if (warp == 3) {
+      // ------------------------------------------------------------ second MMA issuer (query tile 1)
+      const bool leader = elect_one();
+      mbar_wait(q_full, 0);
+      if (RELPOS) mbar_wait(t_done, 0);  // table products (issued by warp 1) drained out of the S / O columns
       tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      issue_s(0, 1);
-      issue_s(1, 1);
-      if (leader) umma_commit(&k_empty[0]);
-      __syncwarp();
-      for (int j = 0; j < ns; ++j) {
-        const int vst = (j >> 1) % NS;
-        const uint32_t vph = (uint32_t)((j >> 1) / NS) & 1u;
-        const bool more = j + 2 < ns;
-        const uint32_t sv = smem_u32(smem + Cfg::OFF_V + vst * Cfg::TILE_BYTES) + (j & 1) * 8192;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (leader) F4_TRACE(2, j, 4 * t);
-          mbar_wait(&p_full[t * 2 + (j & 1)], (uint32_t)(j >> 1) & 1u);
-          if (leader) F4_TRACE(2, j, 4 * t + 1);
-          if (t == 0) {
-            if ((j & 1) == 0) mbar_wait(&v_full[vst], vph);
-            if (more && (j & 1) == 0) {  // step j + 2 opens K tile (j + 2) / 2
-              const int kt = (j + 2) >> 1;
-              mbar_wait(&k_full[kt % NS], (uint32_t)(kt / NS) & 1u);
-            }
-          }
-          tc_fence_after();
-          if (leader) {
-            const uint64_t vd = make_sdesc_sw128(sv, 16384, 1024);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)  // 64 keys, 16 per MMA; P: 8 TMEM columns per step; V: 2048 B per step
-              umma_bf16_ts(tmem_base + Cfg::COL_O + t * HD, tmem_base + t * 128 + (j & 1) * 64 + ks * 8,
-                           vd + (uint32_t)(ks * (2048 >> 4)), idesc_pv, (j | ks) != 0);
-            umma_commit(&pv_done[t]);
-            if (j == ns - 1) umma_commit(&o_full[t]);
-          }
-          __syncwarp();
-          if (leader) F4_TRACE(2, j, 4 * t + 2);
-          if (more) issue_s(t, j + 2);  // reuses the score buffer step j just released (behind its P V in the pipe)
-          if (leader) F4_TRACE(2, j, 4 * t + 3);
-        }
-        if (leader) {
-          if (j & 1) umma_commit(&v_empty[vst]);                       // both halves of the V tile consumed
-          if (more && (j & 1)) umma_commit(&k_empty[((j + 2) >> 1) % NS]);  // both halves of K tile (j + 2) / 2 issued
-        }
-        __syncwarp();
-      }
+      mma_main(1, leader);
     }
   } else {
     // ------------------------------------------------------------ softmax / correction / output
@@ -431,7 +445,10 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           const float m_new = need ? m_chunk : m_ref;
           const float alpha = ex2_approx(m_ref - m_new);  // 1 for lanes that did not need it, 0 on the very first chunk
           if (j > 0) {
-            mbar_wait(&pv_done[t], (uint32_t)(j - 1) & 1u);
+            // P_t(j-1) V must have landed in O.  It was issued ahead of S_t(j+1): wait for that score tile (a peek, the
+            // barrier is waited on again at step j + 1); the last step has no such tile and uses the explicit commit.
+            if (j + 1 < ns) mbar_wait(&s_full[t * 2 + ((j + 1) & 1)], (uint32_t)((j + 1) >> 1) & 1u);
+            else mbar_wait(&pv_done[t], 0);
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k) {

@@ -46,12 +46,12 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN >= 32 ? 2 * BN : 32;
 };
 
-// Exact-erf GELU (nn.GELU(), M/common.py:13-26): x (0.5 + 0.5 erf(x / sqrt 2)) = x (0.5 + xc Q(xc^2)) with
-// xc = clamp(x, +-3 sqrt 2) and Q a degree-8 fit of 0.5 erf(x / sqrt 2) / x in x^2 (saturated beyond: 1 - erf(3) = 2.2e-5).
-// 11 FMA-pipe operations and no MUFU: the GELU epilogue has to stay under the main-loop time of the next tile (erff()
-// costs ~25 operations, a rcp/ex2 formulation 2 MUFU per element -- both measured slower; the packed fp32x2 forms issue
-// at half rate, so the operation count is what matters -- profiles/r01z_ncu_gemm_gelu_summary.txt).  |error| <= 6.3e-5
-// on GELU, far below the bf16 rounding of the stored activation.
+// Exact-erf GELU (nn.GELU(), M/common.py:13-26): x (0.5 + 0.5 erf(x / sqrt 2)) = x sat(0.5 + x Q(t)), t = min(x^2, 18), Q a
+// degree-8 fit of 0.5 erf(x / sqrt 2) / x in x^2 on |x| <= 3 sqrt 2; beyond that x Q(18) leaves [-0.5, 0.5] and the
+// saturating FMA (free on the FMA pipe) pins the factor to exactly 0 or 1.  11 FMA-pipe operations + 1 min and no MUFU:
+// the GELU epilogue has to stay under the main-loop time of the next tile and is issue-bound (two epilogue warps per
+// scheduler; erff() costs ~25 operations, a rcp/ex2 formulation 2 MUFU per element -- both measured slower;
+// profiles/r01z_ncu_gemm_gelu_summary.txt).  |error| <= 4.8e-5 on GELU, far below the bf16 rounding of the stored activation.
 #define WM_GELU_C0 0.3988664448261261f
 #define WM_GELU_C1 -0.06624268740415573f
 #define WM_GELU_C2 0.00973955076187849f
@@ -63,8 +63,7 @@ struct GemmCfg {
 #define WM_GELU_C8 4.543853834859668e-11f
 #define WM_GELU_LIM 4.242640687119285f
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float xc = fminf(fmaxf(x, -WM_GELU_LIM), WM_GELU_LIM);
-  const float t = xc * xc;
+  const float t = fminf(x * x, WM_GELU_LIM * WM_GELU_LIM);
   float q = fmaf(WM_GELU_C8, t, WM_GELU_C7);
   q = fmaf(q, t, WM_GELU_C6);
   q = fmaf(q, t, WM_GELU_C5);
@@ -73,7 +72,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
   q = fmaf(q, t, WM_GELU_C2);
   q = fmaf(q, t, WM_GELU_C1);
   q = fmaf(q, t, WM_GELU_C0);
-  return x * fmaf(xc, q, 0.5f);
+  return x * __saturatef(fmaf(x, q, 0.5f));
 }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -81,10 +80,10 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 // Two GELUs at once on the packed fp32x2 FMA path of sm_100 (FFMA2 / FMUL2; common.cuh)
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
-  const float c0 = fminf(fmaxf(x0, -WM_GELU_LIM), WM_GELU_LIM);
-  const float c1 = fminf(fmaxf(x1, -WM_GELU_LIM), WM_GELU_LIM);
-  const uint64_t xc = pk2(c0, c1);
-  const uint64_t t = mul2(xc, xc);
+  const uint64_t xp = pk2(x0, x1);
+  float t0, t1;
+  unpk2(mul2(xp, xp), t0, t1);
+  const uint64_t t = pk2(fminf(t0, WM_GELU_LIM * WM_GELU_LIM), fminf(t1, WM_GELU_LIM * WM_GELU_LIM));
   uint64_t q = fma2(pk2(WM_GELU_C8, WM_GELU_C8), t, pk2(WM_GELU_C7, WM_GELU_C7));
   q = fma2(q, t, pk2(WM_GELU_C6, WM_GELU_C6));
   q = fma2(q, t, pk2(WM_GELU_C5, WM_GELU_C5));
@@ -93,8 +92,10 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   q = fma2(q, t, pk2(WM_GELU_C2, WM_GELU_C2));
   q = fma2(q, t, pk2(WM_GELU_C1, WM_GELU_C1));
   q = fma2(q, t, pk2(WM_GELU_C0, WM_GELU_C0));
-  const uint64_t r = mul2(pk2(x0, x1), fma2(xc, q, pk2(0.5f, 0.5f)));
-  unpk2(r, x0, x1);
+  float q0, q1;
+  unpk2(q, q0, q1);
+  x0 *= __saturatef(fmaf(x0, q0, 0.5f));
+  x1 *= __saturatef(fmaf(x1, q1, 0.5f));
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {

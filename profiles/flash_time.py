@@ -24,4 +24,4 @@ for H, hd, relpos in ((12, 64, 1), (8, 128, 0)):
         f()
     e.record(); torch.cuda.synchronize()
     res.append(f"hd{hd}{'+relpos' if relpos else ''}: {s.elapsed_time(e) / 10:.4f} ms")
-print(os.environ.get("WM_LIB_NAME", "libwm_b200.so"), " | ".join(res))
+print(os.environ.get("WM_LIB_NAME", "libwm_b200.so"), "flash_version", os.environ.get("WM_FLASH_VERSION", "default"), " | ".join(res))

@@ -219,9 +219,10 @@ def test_attn_flash_rising_maxima(hd, flash_version):
     assert (out.float() - ref).abs().max().item() < 3e-2
 
 
-@pytest.fixture(params=[5, 4, 3, 2, 1])
+@pytest.fixture(params=[6, 5, 4, 3, 2, 1])
 def flash_version(request):
-    """All flash-attention kernel generations stay parity-checked (4 = default)."""
+    """All flash-attention kernel generations stay parity-checked (4 = default; 6 = v4 + the three-tile kernel for
+    head dim 64 with rel-pos)."""
     from wildlifemapper_b200 import lib
     lib.call("wm_set_flash_version", request.param)
     yield request.param
@@ -256,6 +257,30 @@ def test_attn_flash_global_relpos(flash_version, hd):
     q, k, v = sp(qkv[:, :D]), sp(qkv[:, D:2 * D]), sp(qkv[:, 2 * D:])
     ref = ref_attention(q, k, v, scale, relpos_bias(q, rel_h, rel_w, 64)).transpose(1, 2).reshape(B * T, D)
     assert (out.float() - ref).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("version", [6, 4])
+def test_attn_flash_global_relpos_peaky(version):
+    """Peaky logits (std ~ 6 in log2 units, strong rel-pos tables): the reference maximum of a row is raised many times
+    along the 4096 keys, so the O / l / P rescale path of the lazy softmax is exercised in the rel-pos kernels too."""
+    from wildlifemapper_b200 import lib
+    lib.call("wm_set_flash_version", version)
+    try:
+        B, H, T, hd = 1, 2, 4096, 64
+        D = H * hd
+        qkv = rnd(B * T, 3 * D, seed=41, scale=2.2)
+        rel_h, rel_w = rnd(127, hd, seed=42, scale=0.6), rnd(127, hd, seed=43, scale=0.6)
+        table = torch.zeros(256, hd, device=DEV, dtype=torch.bfloat16)
+        table[:127], table[128:255] = rel_h, rel_w
+        out = torch.zeros(B * T, D, device=DEV, dtype=torch.bfloat16)
+        scale = hd ** -0.5
+        ops.attn_flash(qkv, 0, qkv, D, qkv, 2 * D, table, out, B, H, T, T, hd, scale)
+        sp = lambda t: t.reshape(B, T, H, hd).transpose(1, 2)
+        q, k, v = sp(qkv[:, :D]), sp(qkv[:, D:2 * D]), sp(qkv[:, 2 * D:])
+        ref = ref_attention(q, k, v, scale, relpos_bias(q, rel_h, rel_w, 64)).transpose(1, 2).reshape(B * T, D)
+        assert rel_err(out, ref) < 2e-2
+    finally:
+        lib.call("wm_set_flash_version", 4)
 
 
 @pytest.fixture(params=[2, 1])

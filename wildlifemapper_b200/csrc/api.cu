@@ -150,7 +150,7 @@ int wm_set_option(const char* name, int value) {
   return fail(WM_ERR_SHAPE, "wm_set_option: unknown option '%s'", n.c_str());
 }
 int wm_set_flash_version(int version) {
-  if (version < 1 || version > 5) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 1 .. 5");
+  if (version < 1 || version > 6) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 1 .. 6");
   g_flash_version = version;
   return WM_OK;
 }
@@ -280,9 +280,9 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
                   int H, int Tq, int Tk, int hd, float scale, void* stream) {
   if (int rc = ensure_device()) return rc;
   if (B <= 0 || H <= 0 || (hd != 64 && hd != 80 && hd != 128)) return fail(WM_ERR_SHAPE, "wm_attn_flash: head dim must be 64, 80 or 128");
-  if (hd == 80 && (g_flash_version < 3 || (Tq % 256 != 0 && g_flash_version != 4))) return fail(WM_ERR_SHAPE, "wm_attn_flash: head dim 80 needs the v3 / v4 kernel (Tq %% 256 == 0)");
+  if (hd == 80 && (g_flash_version < 3 || (Tq % 256 != 0 && g_flash_version != 4 && g_flash_version != 6))) return fail(WM_ERR_SHAPE, "wm_attn_flash: head dim 80 needs the v3 / v4 kernel (Tq %% 256 == 0)");
   const bool ragged = (Tq % 256 != 0) || (Tk % 128 != 0);  // only the v4 kernel masks ragged tiles (no rel-pos)
-  if (ragged && (g_flash_version != 4 || rel_table != nullptr || Tq < 1 || Tk < 1))
+  if (ragged && ((g_flash_version != 4 && g_flash_version != 6) || rel_table != nullptr || Tq < 1 || Tk < 1))
     return fail(WM_ERR_SHAPE, "wm_attn_flash: Tq %% 256 != 0 or Tk %% 128 != 0 needs the v4 kernel without rel-pos");
   if (!ragged && (Tq % 128 || Tk % 128 || Tk < 128)) return fail(WM_ERR_SHAPE, "wm_attn_flash: Tq, Tk must be multiples of 128");
   if ((int64_t)B * Tq > q_rows || (int64_t)B * Tk > k_rows || (int64_t)B * Tk > v_rows) return fail(WM_ERR_SHAPE, "wm_attn_flash: rows");
@@ -290,7 +290,8 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || !aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_attn_flash: alignment");
   if (B > 65535 || H > 65535) return fail(WM_ERR_SHAPE, "wm_attn_flash: grid too large");
   const bool v5 = (g_flash_version == 5) && (Tq % 256 == 0);
-  const bool v4 = (g_flash_version == 4);
+  const bool v6 = (g_flash_version == 6);  // v4 everywhere except the three-tile kernel for head dim 64 + rel-pos
+  const bool v4 = (g_flash_version == 4) || v6;
   const bool v3 = v4 || ((g_flash_version == 3 || v5) && (Tq % 256 == 0));  // (v4 / v5 share v3's tensor maps)
   const bool v2 = (g_flash_version == 2) && (Tq % 256 == 0);
   const uint32_t kv_box = v2 ? 64 : 128;
@@ -310,6 +311,7 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldo = (int)ldo;
   p.use_relpos = rel_table != nullptr;
   p.turns = g_flash_turns;
+  if (v6 && p.use_relpos && hd == 64) return check_launch(wm::flash6_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v6)");
   if (v5) return check_launch(wm::flash5_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v5)");
   if (v4) return check_launch(wm::flash4_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v4)");
   if (v3) return check_launch(wm::flash3_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v3)");

@@ -56,6 +56,8 @@ int flash4_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
                     const FlashParams& p, int hd, cudaStream_t st);
 int flash5_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                     const FlashParams& p, int hd, cudaStream_t st);
+int flash6_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
+                    const FlashParams& p, int hd, cudaStream_t st);
 int flash3_read_trace(unsigned long long* host_out);
 int flash4_read_trace(unsigned long long* host_out);
 int window2_read_trace(unsigned long long* host_out);  // diagnostics build (-DWM_F3_TRACE) only

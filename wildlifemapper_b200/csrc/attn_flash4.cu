@@ -31,6 +31,19 @@ __device__ unsigned long long g_f4_trace[3][64][8];
 #define F4_TRACE(role, j, ev) do { } while (0)
 #endif
 
+// ablation builds (profiles/run_flash_ablation.sh; results are wrong on purpose): -DWM_F4_NO_EX2 replaces the exp2 of the
+// hot loop by one FMA-pipe operation, -DWM_F4_ONE_MMA issues one MMA per group, -DWM_F4_SKELETON keeps only the barrier protocol
+#ifdef WM_F4_ONE_MMA   // one tcgen05.mma per score tile / P V group instead of four
+#define F4_MMA_STEPS 1
+#else
+#define F4_MMA_STEPS 4
+#endif
+#ifdef WM_F4_NO_EX2
+#define F4_EX2(x) ((x) * 0.0009765625f + 1.0f)
+#else
+#define F4_EX2(x) ex2_approx(x)
+#endif
+
 constexpr int F4_THREADS = 384;
 constexpr float F4_LOG2E = 1.4426950408889634f;
 constexpr float F4_TAU = 8.0f;  // lazy-rescale threshold (log2 units): p <= 2^8 between rescales
@@ -149,7 +162,7 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           const uint64_t qd = make_sdesc_sw128(sq + t * Cfg::TILE_BYTES, 16, 1024);
           const uint64_t kd = make_sdesc_sw128(smem_u32(smem + Cfg::OFF_K + kst * Cfg::TILE_BYTES) + (step & 1) * 8192, 16, 1024);
 #pragma unroll
-          for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+          for (int ks = 0; ks < (F4_MMA_STEPS == 4 ? Cfg::KSTEPS : 1); ++ks) {
             const uint32_t off = (uint32_t)((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);  // address field is bytes >> 4
             umma_bf16(tmem_base + t * 128 + (step & 1) * 64, qd + off, kd + off, idesc_s, ks != 0);
           }
@@ -183,7 +196,7 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         if (leader) {
           const uint64_t vd = make_sdesc_sw128(sv, 16384, 1024);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)  // 64 keys, 16 per MMA; P: 8 TMEM columns per step; V: 2048 B per step
+          for (int ks = 0; ks < F4_MMA_STEPS; ++ks)  // 64 keys, 16 per MMA; P: 8 TMEM columns per step; V: 2048 B per step
             umma_bf16_ts(tmem_base + Cfg::COL_O + t * HD, tmem_base + t * 128 + (j & 1) * 64 + ks * 8,
                          vd + (uint32_t)(ks * (2048 >> 4)), idesc_pv, (j | ks) != 0);
           // P_t(j) V complete: only the rare rescale path of step j + 1 needs it; while score tiles are still being
@@ -374,6 +387,12 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       // chunk 0 is processed.  Each chunk is first evaluated OPTIMISTICALLY against the current reference maximum;
       // only if some row of the warp exceeds it by more than 2^TAU is the reference raised (O, l and the chunk of P
       // already written are rescaled) and the chunk recomputed from the registers that still hold it.
+#ifdef WM_F4_SKELETON  // ablation: barrier / MMA skeleton only -- no score loads, no softmax arithmetic, no P stores
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t * 2 + (j & 1)]);
+      continue;
+#endif
       uint32_t v[2][32];
       tmem_ld32(sj, v[0]);
       tmem_ld32(sj + 32, v[1]);
@@ -432,7 +451,7 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           for (int i = 0; i < 16; ++i) {
             float a0, a1;
             unpk2(yp[i], a0, a1);
-            const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+            const float e0 = F4_EX2(a0), e1 = F4_EX2(a1);
             cs2[i & 1] = add2(cs2[i & 1], pk2(e0, e1));
             pk[i] = pack_bf16(e0, e1);
           }
@@ -491,7 +510,7 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
               yp = fma2(vp, c1p, dp);
             float a0, a1;
             unpk2(yp, a0, a1);
-            const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+            const float e0 = F4_EX2(a0), e1 = F4_EX2(a1);
             cs2[i & 1] = add2(cs2[i & 1], pk2(e0, e1));
             pk[i] = pack_bf16(e0, e1);
           }

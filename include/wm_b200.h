@@ -39,15 +39,13 @@ int wm_version(void);
 const char* wm_last_error(void);
 /* 0 if the current device is sm_100 and the driver exposes cuTensorMapEncodeTiled */
 int wm_device_check(void);
-/* Select the flash-attention kernel generation used by wm_attn_flash: 6 (v4 for every shape, except that head dim 64 with
- * rel-pos -- the global attention of ViT-B / ViT-L -- runs THREE query tiles per CTA: three softmax warps per scheduler),
- * 4 (default; 64-key steps over double-buffered score
- * tiles, P kept in tensor memory, two query tiles per CTA), 5 (v4 with two threads per query row / 16 softmax warps:
- * measured 9 % slower than v4, kept for A/B), 3 (128-key tiles, single score buffer per query tile),
- * 2 (64-key tiles, P staged in shared memory) or 1 (first-generation kernel; also the path taken when Tq % 256 != 0).
- * Kept selectable for A/B measurements. */
+/* Select the flash-attention kernel generation used by wm_attn_flash: 4 (default: 64-key steps over double-buffered score
+ * tiles, P kept in tensor memory, two query tiles per CTA, one MMA issuer warp per tile), 6 (v4 for every shape, except that
+ * head dim 64 with rel-pos runs THREE query tiles per CTA -- an experiment, +0.75 %), 3 (128-key tiles, single score
+ * buffer per query tile: the predecessor of v4) or 1 (first-generation kernel, P staged in shared memory).  Kept selectable
+ * for A/B measurements; generations 2 and 5 were measured slower and removed. */
 int wm_set_flash_version(int version);
-/* Tuning knobs (for A/B measurements): "flash_version" (1..6), "flash_turns" (0|1: v3 softmax warpgroups take turns
+/* Tuning knobs (for A/B measurements): "flash_version" (1 | 3 | 4 | 6), "flash_turns" (0|1: v3 softmax warpgroups take turns
  * on the MUFU), "gemm_pairs" (0|1: large GEMMs on the CTA-pair kernel), "window_version" (1|2: windowed-attention kernel generation). */
 int wm_set_option(const char* name, int value);
 /* Diagnostics build only (csrc/build.sh with -DWM_F3_TRACE): copy the SM-clock event trace of CTA (0,0,0) of the last

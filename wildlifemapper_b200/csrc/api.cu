@@ -150,7 +150,7 @@ int wm_set_option(const char* name, int value) {
   return fail(WM_ERR_SHAPE, "wm_set_option: unknown option '%s'", n.c_str());
 }
 int wm_set_flash_version(int version) {
-  if (version < 1 || version > 6) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 1 .. 6");
+  if (version != 1 && version != 3 && version != 4 && version != 6) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 1, 3, 4 or 6");
   g_flash_version = version;
   return WM_OK;
 }
@@ -289,12 +289,10 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   if (q_col0 + H * hd > q_width || k_col0 + H * hd > k_width || v_col0 + H * hd > v_width) return fail(WM_ERR_SHAPE, "wm_attn_flash: columns");
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || !aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_attn_flash: alignment");
   if (B > 65535 || H > 65535) return fail(WM_ERR_SHAPE, "wm_attn_flash: grid too large");
-  const bool v5 = (g_flash_version == 5) && (Tq % 256 == 0);
   const bool v6 = (g_flash_version == 6);  // v4 everywhere except the three-tile kernel for head dim 64 + rel-pos
   const bool v4 = (g_flash_version == 4) || v6;
-  const bool v3 = v4 || ((g_flash_version == 3 || v5) && (Tq % 256 == 0));  // (v4 / v5 share v3's tensor maps)
-  const bool v2 = (g_flash_version == 2) && (Tq % 256 == 0);
-  const uint32_t kv_box = v2 ? 64 : 128;
+  const bool v3 = v4 || (g_flash_version == 3 && (Tq % 256 == 0));  // (v4 shares v3's tensor maps)
+  const uint32_t kv_box = 128;
   CUtensorMap tq, tk, tv, trel;
   if (int rc = make_map_2d(&tq, q, (uint64_t)q_rows, (uint64_t)q_width, (uint64_t)ldq, 128, "wm_attn_flash(q)")) return rc;
   if (int rc = make_map_2d(&tk, k, (uint64_t)k_rows, (uint64_t)k_width, (uint64_t)ldk, kv_box, "wm_attn_flash(k)")) return rc;
@@ -303,7 +301,7 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   if (rel_table != nullptr) {
     if ((hd != 64 && !(hd == 80 && v3)) || Tq != 4096 || Tk != 4096)
       return fail(WM_ERR_SHAPE, "wm_attn_flash: rel-pos needs hd 64 (or 80 on the v3 kernel) and 64x64 tokens");
-    if (int rc = make_map_2d(&trel, rel_table, 256, (uint64_t)hd, (uint64_t)hd, (v2 || v3) ? 16 : 256, "wm_attn_flash(rel)")) return rc;
+    if (int rc = make_map_2d(&trel, rel_table, 256, (uint64_t)hd, (uint64_t)hd, v3 ? 16 : 256, "wm_attn_flash(rel)")) return rc;
   }
   wm::FlashParams p{};
   p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.scale = scale;
@@ -312,10 +310,8 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   p.use_relpos = rel_table != nullptr;
   p.turns = g_flash_turns;
   if (v6 && p.use_relpos && hd == 64) return check_launch(wm::flash6_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v6)");
-  if (v5) return check_launch(wm::flash5_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v5)");
   if (v4) return check_launch(wm::flash4_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v4)");
   if (v3) return check_launch(wm::flash3_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v3)");
-  if (v2) return check_launch(wm::flash2_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v2)");
   return check_launch(wm::flash_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash");
 }
 

@@ -47,14 +47,10 @@ struct FlashParams {
 int flash_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                    const FlashParams& p, int hd, cudaStream_t st);
 
-int flash2_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
-                    const FlashParams& p, int hd, cudaStream_t st);
 int flash3_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                     const FlashParams& p, int hd, cudaStream_t st);
 
 int flash4_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
-                    const FlashParams& p, int hd, cudaStream_t st);
-int flash5_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                     const FlashParams& p, int hd, cudaStream_t st);
 int flash6_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                     const FlashParams& p, int hd, cudaStream_t st);

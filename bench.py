@@ -28,7 +28,7 @@ MODEL_CONFIGS = {"vit_b": (768, 12, 12, (2, 5, 8, 11)), "vit_l": (1024, 24, 16, 
 # algorithmic GFLOP per tile (SURVEY.md section 8d / BASELINE.md section 3)
 GFLOP_PER_TILE = {"vit_b": 1085.0, "vit_l": 2988.7, "vit_h": 5797.8}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (one `ncu --set full` capture, see profiles/)
-NCU_TRAFFIC = {"gemm": 757.6e6}
+NCU_TRAFFIC = {"gemm": 752.8e6}
 METRIC = "tiles_per_sec"
 UNIT = "tiles/s"
 
@@ -308,7 +308,7 @@ def run_b200(args):
         roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tflops"], "traffic": NCU_TRAFFIC.get(name),
                 "traffic_note": "DRAM read+write bytes of the qkv-shaped launch (M=131072, N=2304, K=768; algorithmic "
-                                "809 MB) from ncu --set full, profiles/r01j_ncu_gemm_q512_summary.txt",
+                                "809 MB) from ncu --set full, profiles/r01z_ncu_gemm_qkv_summary.txt (the tail of the output is still in L2 when the kernel ends)",
                 "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
                 "share_of_step": r["ms"] / ms_eager, "launches_per_step": r["launches"] / args.steps,
                 "avg_launch_ms": r["ms"] / r["launches"],

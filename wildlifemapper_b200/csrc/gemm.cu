@@ -118,7 +118,10 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // barrier lives in the leader CTA of the pair (2-CTA kernel, non-leader CTA).
 // STAGE_BUFS = 4 KB staging buffers per warp (2 in the CTA-pair kernel): with two, single-output stores alternate between
 // them (`sbuf`, carried across tiles) and only wait for the store before the previous one.
-template <int BN, int STAGE_BUFS>
+// ACT >= 0 / FAST (1: bf16 output, 2: fp32 output): compile-time activation and "single output through the TMA path" (the CTA-pair kernel is instantiated
+// for the hot combinations: the epilogue of the GELU GEMM is its bottleneck, and with every activation and output path
+// inlined four times per tile the kernel was 155 KB of code with 8-12 % instruction-fetch stalls in the epilogue warps).
+template <int BN, int STAGE_BUFS, int ACT = -1, int FAST = 0>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtensorMap* tc16, const CUtensorMap* tc32,
                                               uint8_t* stage, uint32_t tmem_acc, int tile_row0, int tile_n0, int warp,
                                               int lane, uint64_t* tempty, bool remote, uint32_t& sbuf) {
@@ -145,11 +148,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
     return;
   }
   const bool row_ok = row < p.M;
-  if (p.tma_out) {
+  const int act = ACT >= 0 ? ACT : p.act;
+  if (FAST || p.tma_out) {
     const uint32_t st_row = smem_u32(stage) + (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
     const float* res_row = (p.residual != nullptr && !p.res_inplace) ? p.residual + (size_t)(row % p.res_mod) * p.ldr : nullptr;
-    const bool alt = STAGE_BUFS == 2 && p.tma_out == 1;  // single output: alternate the warp's two staging buffers
+    const bool alt = STAGE_BUFS == 2 && (FAST || p.tma_out == 1);  // single output: alternate the warp's two staging buffers
     uint32_t v[2][32];
     float4 bq[2][8];  // bias of a chunk (the same 32 values in every lane), fetched one chunk ahead of its use
     auto fetch_bias = [&](int c) {
@@ -189,12 +193,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
               if (n0 + j < p.N) f[j] += __ldg(p.bias + n0 + j);
           }
         }
-        if (p.act == 1) {
+        if (act == 1) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) gelu_erf2(f[2 * j], f[2 * j + 1]);
-        } else if (p.act != 0) {
+        } else if (act != 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], act);
         }
         if (res_row != nullptr && row_ok) {  // residual that is not updated in place (pos-embed broadcast, decoder): row-per-lane reads
           if (full) {
@@ -209,7 +213,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
               if (n0 + j < p.N) f[j] += __ldg(res_row + n0 + j);
           }
         }
-        if (p.out_f32 != nullptr) {
+        if (FAST != 1 && p.out_f32 != nullptr) {
           // ---- fp32 output: 32 columns = one 128-byte swizzled row per lane
           // the earlier stores of this warp have finished reading the staging buffer about to be rewritten
           const uint32_t off32 = alt ? (sbuf & 1u) * 4096u : 0u;
@@ -231,7 +235,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
           }
           ++sbuf;
         }
-        if (p.out_bf16 != nullptr) {
+        if (FAST != 2 && p.out_bf16 != nullptr) {
           // ---- bf16 output: two chunks share one 128-byte row (64 columns): even chunk -> 16-byte pieces 0..3, odd -> 4..7.
           // An unpaired last chunk only happens at the right edge of the matrix, where TMA clips the unwritten half.
           // With both outputs (tma_out == 2, CTA-pair kernel) the bf16 rows use the warp's second staging buffer; the
@@ -263,6 +267,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
     }
     return;
   }
+  if (FAST) return;  // (compile time: the generic path below is not instantiated for the fast variants)
   // generic path (ragged or unaligned outputs -- decoder heads N = 8, N = 4 -- and dual fp32 + bf16 outputs): scalar
   // row-per-lane epilogue
   const float* res_row = (p.residual != nullptr && row_ok) ? p.residual + (size_t)(row % p.res_mod) * p.ldr : nullptr;
@@ -280,7 +285,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
       for (int j = 0; j < 32; ++j) {
         f[j] = __uint_as_float(v[j]);
         if (p.bias != nullptr && n0 + j < p.N) f[j] += __ldg(p.bias + n0 + j);
-        f[j] = apply_act(f[j], p.act);
+        f[j] = apply_act(f[j], act);
       }
       if (vec) {
         if (res_row != nullptr) {
@@ -472,6 +477,7 @@ struct Gemm2Cfg {
   static constexpr int TMEM_COLS = 512;  // 2 accumulator stages x 256 columns
 };
 
+template <int ACT, int FAST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_c16, const __grid_constant__ CUtensorMap tmap_c32,
@@ -581,7 +587,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int n_blk = t % num_n, m_blk = t / num_n;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN, 2>(p, &tmap_c16, &tmap_c32, stage_buf, tmem_base + as * BN, m_blk * 256 + (int)rank * 128, n_blk * BN,
+      epilogue_tile<BN, 2, ACT, FAST>(p, &tmap_c16, &tmap_c32, stage_buf, tmem_base + as * BN, m_blk * 256 + (int)rank * 128, n_blk * BN,
                            warp, lane, &tempty_bar[as], rank != 0, sbuf);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -596,20 +602,30 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
-static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc16, const CUtensorMap& tc32,
-                        const GemmParams& p, int num_sms, cudaStream_t st) {
+template <int ACT, int FAST>
+static int launch_gemm2_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc16, const CUtensorMap& tc32,
+                                const GemmParams& p, int num_sms, cudaStream_t st) {
   using Cfg = Gemm2Cfg;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm2_bf16_kernel<ACT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+        cudaSuccess)
       return WM_ERR_CUDA;
     attr_set = true;
   }
   const int tiles = ((p.M + 255) / 256) * (p.N / 256);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm2_bf16_kernel<<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, st>>>(ta, tw, tc16, tc32, p);
+  gemm2_bf16_kernel<ACT, FAST><<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, st>>>(ta, tw, tc16, tc32, p);
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc16, const CUtensorMap& tc32,
+                        const GemmParams& p, int num_sms, cudaStream_t st) {
+  // lin1 + GELU (epilogue-bound) gets its own instantiation: -9 % (0.552 -> 0.501 ms at batch 32).  The epilogue-free
+  // shapes are main-loop bound and measured 0-1 % slower when specialised the same way, so they stay on the general kernel.
+  if (p.tma_out == 1 && p.act == 1 && p.out_bf16 != nullptr) return launch_gemm2_variant<1, 1>(ta, tw, tc16, tc32, p, num_sms, st);
+  return launch_gemm2_variant<-1, 0>(ta, tw, tc16, tc32, p, num_sms, st);
 }
 
 template <int BN>

@@ -133,8 +133,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
   const int wcol0 = half * (BN / 2);     // first tile column of this warp
   const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)wcol0;
   // number of chunks of this warp that lie (at least partly) inside N: warp-uniform
-  int nact = (p.N - (tile_n0 + wcol0) + 31) / 32;
-  nact = nact < 0 ? 0 : (nact > NCH ? NCH : nact);
+  // (the CTA-pair kernel only runs with N % 256 == 0: no ragged right edge, and the dead edge code stays out of it)
+  constexpr bool kWholeTiles = STAGE_BUFS == 2;
+  int nact = NCH;
+  if (!kWholeTiles) {
+    nact = (p.N - (tile_n0 + wcol0) + 31) / 32;
+    nact = nact < 0 ? 0 : (nact > NCH ? NCH : nact);
+  }
   auto release = [&]() {  // this warp has read its share of the accumulator
     tc_fence_before();
     __syncwarp();
@@ -179,7 +184,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[c & 1][j]);
-        const bool full = n0 + 32 <= p.N;  // (N % 8 == 0 on this path; partial chunks only at the right edge)
+        const bool full = kWholeTiles || n0 + 32 <= p.N;  // (N % 8 == 0 on this path; partial chunks only at the right edge)
         if (p.bias != nullptr) {
           if (full) {
 #pragma unroll

@@ -115,7 +115,8 @@ def test_patchify_and_gray():
     assert (gray.float() - g).abs().max().item() < 0.02
 
 
-@pytest.mark.parametrize("R,C,dt", [(1024, 4096, torch.bfloat16), (4096, 256, torch.float32), (100, 70, torch.float32)])
+@pytest.mark.parametrize("R,C,dt", [(1024, 4096, torch.bfloat16), (4096, 256, torch.float32), (100, 70, torch.float32),
+                                     (1024, 2048, torch.bfloat16), (100, 70, torch.bfloat16), (67, 33, torch.bfloat16)])
 def test_transpose(R, C, dt):
     x = rnd(3, R, C, seed=16, dtype=dt)
     out = torch.empty(3, C, R, device=DEV, dtype=dt)

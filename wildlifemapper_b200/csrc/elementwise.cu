@@ -144,9 +144,39 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in
   }
 }
 
+// 2-byte elements, R and C even: 64 x 64 tiles moved as 4-byte words on both sides (a 32 x 32 tile of 2-byte elements reads
+// and writes 64 bytes per warp access: half of a 128-byte line).  Word (r, c/2) of the input holds columns c, c+1 of row r;
+// word (c, r/2) of the output holds rows r, r+1 of column c.
+__global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int R, int C) {
+  __shared__ uint16_t tile[64][66];  // [row][col], row stride 33 words: conflict-free on both passes
+  const size_t boff = (size_t)blockIdx.z * R * C;
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 words x 8 rows
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + 2 * tx;
+    if (r < R && c < C) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(in + boff + (size_t)r * C + c);
+      *reinterpret_cast<uint32_t*>(&tile[ty + 8 * i][2 * tx]) = w;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + 2 * tx;
+    if (r < R && c < C) {
+      const uint32_t w = (uint32_t)tile[2 * tx][ty + 8 * i] | ((uint32_t)tile[2 * tx + 1][ty + 8 * i] << 16);
+      *reinterpret_cast<uint32_t*>(out + boff + (size_t)c * R + r) = w;
+    }
+  }
+}
+
 int transpose_launch(const void* in, void* out, int batch, int R, int C, int elt_bytes, cudaStream_t st) {
   dim3 grid((C + 31) / 32, (R + 31) / 32, batch);
-  if (elt_bytes == 2)
+  if (elt_bytes == 2 && R % 2 == 0 && C % 2 == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 3) == 0)
+    transpose16_kernel<<<dim3((C + 63) / 64, (R + 63) / 64, batch), 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, R, C);
+  else if (elt_bytes == 2)
     transpose_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, R, C);
   else if (elt_bytes == 4)
     transpose_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)in, (uint32_t*)out, R, C);

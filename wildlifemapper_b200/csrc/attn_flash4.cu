@@ -44,6 +44,24 @@ __device__ unsigned long long g_f4_trace[3][64][8];
 #define F4_EX2(x) ex2_approx(x)
 #endif
 
+// exp2 on the FMA / ALU pipes for arguments x <= TAU: 2^x = 2^round(x) * p(x - round(x)), cubic minimax on [-0.5, 0.5]
+// (relative error ~1e-4, below the bf16 rounding of P).  WM_F4_POLY = n sends every n-th PAIR of a 32-score chunk this way
+// (FA4-style MUFU relief).  Measured per launch at batch 32, hd 64 + rel-pos / hd 128 (profiles/flash_time.py, in-run A/B):
+// off 2.827 / 1.728 ms, n = 8: 2.770 / 1.664, n = 6: 2.730 / 1.656, n = 5: 2.929 / 1.717, n = 4: 2.775 / 1.688,
+// n = 3: 2.984 / 1.788, n = 2: 2.987 / 1.826 -- the schedule ptxas finds matters as much as the fraction.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -120.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: round to nearest integer in the mantissa
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.0555041f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+#ifndef WM_F4_POLY
+#define WM_F4_POLY 6
+#endif
+
 constexpr int F4_THREADS = 384;
 constexpr float F4_LOG2E = 1.4426950408889634f;
 constexpr float F4_TAU = 8.0f;  // lazy-rescale threshold (log2 units): p <= 2^8 between rescales
@@ -451,7 +469,8 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           for (int i = 0; i < 16; ++i) {
             float a0, a1;
             unpk2(yp[i], a0, a1);
-            const float e0 = F4_EX2(a0), e1 = F4_EX2(a1);
+            const bool poly = WM_F4_POLY > 0 && (i % (WM_F4_POLY > 0 ? WM_F4_POLY : 1)) == 0;
+            const float e0 = poly ? ex2_poly(a0) : F4_EX2(a0), e1 = poly ? ex2_poly(a1) : F4_EX2(a1);
             cs2[i & 1] = add2(cs2[i & 1], pk2(e0, e1));
             pk[i] = pack_bf16(e0, e1);
           }
@@ -510,7 +529,8 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
               yp = fma2(vp, c1p, dp);
             float a0, a1;
             unpk2(yp, a0, a1);
-            const float e0 = F4_EX2(a0), e1 = F4_EX2(a1);
+            const bool poly = WM_F4_POLY > 0 && (i % (WM_F4_POLY > 0 ? WM_F4_POLY : 1)) == 0;
+            const float e0 = poly ? ex2_poly(a0) : F4_EX2(a0), e1 = poly ? ex2_poly(a1) : F4_EX2(a1);
             cs2[i & 1] = add2(cs2[i & 1], pk2(e0, e1));
             pk[i] = pack_bf16(e0, e1);
           }

@@ -64,7 +64,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
 
 constexpr int F4_THREADS = 384;
 constexpr float F4_LOG2E = 1.4426950408889634f;
-constexpr float F4_TAU = 8.0f;  // lazy-rescale threshold (log2 units): p <= 2^8 between rescales
+constexpr float F4_TAU = 16.0f;  // lazy-rescale threshold (log2 units): p <= 2^16 between rescales (bf16 P and the fp32 accumulators have the range)
 
 template <int HD, bool RELPOS>
 struct Flash4Cfg {

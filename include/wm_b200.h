@@ -105,10 +105,10 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
                   int64_t v_width, int64_t ldv, int v_col0, const void* rel_table, void* out_bf16, int64_t ldo, int B,
                   int H, int Tq, int Tk, int hd, float scale, void* stream);
 
-/* Fused 14x14 windowed attention on qkv bf16 [B,64,64,3D] (q | k | v, head-major, hd = 64) written straight to
+/* Fused 14x14 windowed attention on qkv bf16 [B,64,64,3D] (q | k | v, head-major, hd = D / H = 64 or 80) written straight to
  * [B,64,64,D]; window partition, zero padding to 70x70, unpartition and crop happen in TMA coordinates.
  * The qkv GEMM must have been run with the k and v biases DROPPED (pad keys, see attn_window.cu).
- * rel_table: bf16 [64, 64]: rows 0..26 = rel_pos_h, 32..58 = rel_pos_w, others 0.
+ * rel_table: bf16 [64, hd]: rows 0..26 = rel_pos_h, 32..58 = rel_pos_w, others 0.
  * Replaces window_partition + Attention.forward + window_unpartition, image_encoder.py:192-199,246-311. */
 int wm_attn_window(const void* qkv, const void* rel_table, void* out_bf16, int B, int H, int D, float scale,
                    void* stream);

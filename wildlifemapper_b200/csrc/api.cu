@@ -343,20 +343,22 @@ int wm_attn_window(const void* qkv, const void* rel_table, void* out_bf16, int B
   wm::WindowParams p{};
   p.B = B; p.H = H; p.scale = scale; p.D = D;
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  if (g_window_version == 2 && hd == 64) {
+  if (g_window_version == 2) {
     // dense 14-wide boxes: a query half is 7 window rows x 14, K / V are the whole 14 x 14 window; zero padding of the
     // 70x70 grid = TMA out-of-bounds fill on loads, the crop back to 64x64 = TMA bounds check on the output store
     const uint32_t box_q[4] = {64, 14, 7, 1};
     const uint32_t box_kv[4] = {64, 14, 14, 1};
     const uint64_t odims[4] = {(uint64_t)D, 64, 64, (uint64_t)B};
     const uint64_t ostrides[3] = {(uint64_t)D * 2, (uint64_t)D * 2 * 64, (uint64_t)D * 2 * 4096};
-    const uint64_t rdims[2] = {64, 64};
-    const uint64_t rstrides[1] = {128};
+    const uint64_t rdims[2] = {(uint64_t)hd, 64};
+    const uint64_t rstrides[1] = {(uint64_t)hd * 2};
     const uint32_t rbox[2] = {64, 27};
     if (int rc = make_map(&tq, qkv, 4, dims, strides, box_q, "wm_attn_window(q)")) return rc;
     if (int rc = make_map(&tkv, qkv, 4, dims, strides, box_kv, "wm_attn_window(kv)")) return rc;
     if (int rc = make_map(&trel, rel_table, 2, rdims, rstrides, rbox, "wm_attn_window(rel)")) return rc;
     if (int rc = make_map(&tout, out_bf16, 4, odims, ostrides, box_q, "wm_attn_window(out)")) return rc;
+    if (hd == 80)  // ViT-H: same structure with two 64-column sub-tiles per operand row
+      return check_launch(wm::window3_dispatch(tq, tkv, trel, tout, p, g_dev.num_sms, (cudaStream_t)stream), "wm_attn_window(v2, hd 80)");
     return check_launch(wm::window2_dispatch(tq, tkv, trel, tout, p, g_dev.num_sms, (cudaStream_t)stream), "wm_attn_window(v2)");
   }
   const uint32_t box_q[4] = {64, 16, 7, 1};

@@ -68,5 +68,7 @@ int window_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtenso
                     cudaStream_t st);
 int window2_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const CUtensorMap& tout,
                      const WindowParams& p, int num_sms, cudaStream_t st);
+int window3_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const CUtensorMap& tout,
+                     const WindowParams& p, int num_sms, cudaStream_t st);
 
 }  // namespace wm

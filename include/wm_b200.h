@@ -39,17 +39,13 @@ int wm_version(void);
 const char* wm_last_error(void);
 /* 0 if the current device is sm_100 and the driver exposes cuTensorMapEncodeTiled */
 int wm_device_check(void);
-/* Select the flash-attention kernel generation used by wm_attn_flash: 4 (default: 64-key steps over double-buffered score
- * tiles, P kept in tensor memory, two query tiles per CTA, one MMA issuer warp per tile), 6 (v4 for every shape, except that
- * head dim 64 with rel-pos runs THREE query tiles per CTA -- an experiment, +0.75 %), 3 (128-key tiles, single score
- * buffer per query tile: the predecessor of v4) or 1 (first-generation kernel, P staged in shared memory).  Kept selectable
- * for A/B measurements; generations 2 and 5 were measured slower and removed. */
+/* Select the flash-attention kernel generation used by wm_attn_flash (A/B measurements; the superseded generations
+ * 1-3, 5 and 6 of round 1 were measured slower and removed). */
 int wm_set_flash_version(int version);
-/* Tuning knobs (for A/B measurements): "flash_version" (1 | 3 | 4 | 6), "flash_turns" (0|1: v3 softmax warpgroups take turns
- * on the MUFU), "gemm_pairs" (0|1: large GEMMs on the CTA-pair kernel), "window_version" (1|2: windowed-attention kernel generation). */
+/* Measurement knobs (atomic, read once per call): "flash_version", "gemm_pairs" (0|1: large GEMMs on the CTA-pair kernel). */
 int wm_set_option(const char* name, int value);
 /* Diagnostics build only (csrc/build.sh with -DWM_F3_TRACE): copy the SM-clock event trace of CTA (0,0,0) of the last
- * v3 / v4 flash-attention launch (whichever generation is selected) to host_out[3][64][8]; WM_ERR_ARCH in the product build. */
+ * flash-attention launch to host_out[3][64][8]; WM_ERR_ARCH in the product build. */
 int wm_debug_flash_trace(uint64_t* host_out_3x64x4);
 /* Same for CTA 0 of the last windowed-attention (v2) launch: host_out[3][64][8]. */
 int wm_debug_window_trace(uint64_t* host_out_3x64x8);
@@ -90,7 +86,8 @@ int wm_transpose(const void* in, void* out, int batch, int R, int C, int elt_byt
  * and, if hfc_img != NULL, the fp32 image [B,1024,1024]. */
 int wm_hfc_finalize(const float* img, const float* low_t, void* patches_bf16, float* hfc_img, int B, void* stream);
 
-/* out_bf16[row, :] = a[row, :] + b[(row % b_mod), :]   (b may be NULL: plain cast).  fp32 in, D % 4 == 0. */
+/* out_bf16[row, :] = a[row, :] + b[(row % b_mod), :]   (b NULL: plain cast; a NULL: batch-broadcast cast of b; not both).
+ * fp32 in, D % 4 == 0. */
 int wm_add_cast(const float* a, const float* b, int b_mod, void* out_bf16, int rows, int D, void* stream);
 
 /* Fused flash attention (tcgen05): out[b*Tq+t, h*hd+d] = softmax_k(scale * q.k [+ rel-pos]) v.

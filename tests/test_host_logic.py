@@ -137,7 +137,17 @@ def _gloo_worker(rank, world, port, q):
     allp = torch.arange(6 * 4 * 6, dtype=torch.float32).view(6, 4, 6)
     allc = torch.tensor([1, 0, 4, 2, 3, 1], dtype=torch.int32)
     p, c, k, kc = gather_detections(allp[lo:hi].clone(), allc[lo:hi].clone(), None, None)
-    q.put((rank, torch.equal(p, allp), torch.equal(c, allc), k is None))
+    # packed variant: the four detection tensors of a rank in one flat buffer, ONE all-gather, split on arrival
+    from wildlifemapper_b200.dist import gather_buffer
+    from wildlifemapper_b200.postprocess import DetectionBuffer
+    B, Q = 3, 4
+    allk = (torch.arange(6 * Q, dtype=torch.int32) * 7 % 5).view(6, Q)
+    allkc = torch.tensor([0, 4, 1, 2, 2, 3], dtype=torch.int32)
+    buf = DetectionBuffer(B, Q, "cpu")
+    buf.packed.copy_(allp[lo:hi]); buf.counts.copy_(allc[lo:hi]); buf.keep_idx.copy_(allk[lo:hi]); buf.keep_cnt.copy_(allkc[lo:hi])
+    gp, gc, gk, gkc = DetectionBuffer.split(gather_buffer(buf), world, B, Q)
+    ok_buf = torch.equal(gp, allp) and torch.equal(gc, allc) and torch.equal(gk, allk) and torch.equal(gkc, allkc)
+    q.put((rank, torch.equal(p, allp), torch.equal(c, allc), k is None and ok_buf))
     dist.destroy_process_group()
 
 

@@ -171,8 +171,6 @@ def test_attn_small(Tq, Tk, hd, H):
 
 @pytest.mark.parametrize("hd,H,T", [(64, 2, 256), (64, 3, 4096), (128, 2, 512), (128, 8, 4096), (80, 3, 1024)])
 def test_attn_flash_plain(hd, H, T, flash_version):
-    if hd == 80 and flash_version < 3:
-        pytest.skip("head dim 80 (ViT-H) is served by the v3 / v4 kernels only")
     B = 2 if T <= 512 else 1
     q = rnd(B * T, H * hd, seed=24)
     kv = rnd(B * T, 2 * H * hd, seed=25)
@@ -220,14 +218,17 @@ def test_attn_flash_rising_maxima(hd, flash_version):
     assert (out.float() - ref).abs().max().item() < 3e-2
 
 
-@pytest.fixture(params=[6, 4, 3, 1])
+FLASH_VERSIONS = [4]  # selectable flash-attention kernel generations (wm_set_flash_version); the first one is the default
+FLASH_DEFAULT = FLASH_VERSIONS[0]
+
+
+@pytest.fixture(params=FLASH_VERSIONS)
 def flash_version(request):
-    """All flash-attention kernel generations stay parity-checked (4 = default; 6 = v4 + the three-tile kernel for
-    head dim 64 with rel-pos)."""
+    """Every selectable flash-attention kernel generation stays parity-checked."""
     from wildlifemapper_b200 import lib
     lib.call("wm_set_flash_version", request.param)
     yield request.param
-    lib.call("wm_set_flash_version", 4)
+    lib.call("wm_set_flash_version", FLASH_DEFAULT)
 
 
 def relpos_bias(q, rel_h, rel_w, S):
@@ -243,8 +244,6 @@ def relpos_bias(q, rel_h, rel_w, S):
 
 @pytest.mark.parametrize("hd", [64, 80])
 def test_attn_flash_global_relpos(flash_version, hd):
-    if hd == 80 and flash_version < 3:
-        pytest.skip("head dim 80 (ViT-H) is served by the v3 / v4 kernels only")
     B, H, T = 2, 3, 4096
     D = H * hd
     qkv = rnd(B * T, 3 * D, seed=26)
@@ -260,7 +259,7 @@ def test_attn_flash_global_relpos(flash_version, hd):
     assert (out.float() - ref).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize("version", [6, 4])
+@pytest.mark.parametrize("version", FLASH_VERSIONS)
 def test_attn_flash_global_relpos_peaky(version):
     """Peaky logits (std ~ 6 in log2 units, strong rel-pos tables): the reference maximum of a row is raised many times
     along the 4096 keys, so the O / l / P rescale path of the lazy softmax is exercised in the rel-pos kernels too."""
@@ -281,20 +280,11 @@ def test_attn_flash_global_relpos_peaky(version):
         ref = ref_attention(q, k, v, scale, relpos_bias(q, rel_h, rel_w, 64)).transpose(1, 2).reshape(B * T, D)
         assert rel_err(out, ref) < 2e-2
     finally:
-        lib.call("wm_set_flash_version", 4)
-
-
-@pytest.fixture(params=[2, 1])
-def window_version(request):
-    """Both windowed-attention kernel generations stay parity-checked (2 = default)."""
-    from wildlifemapper_b200 import lib
-    lib.call("wm_set_option", b"window_version", request.param)
-    yield request.param
-    lib.call("wm_set_option", b"window_version", 2)
+        lib.call("wm_set_flash_version", FLASH_DEFAULT)
 
 
 @pytest.mark.parametrize("B,H,hd", [(1, 2, 64), (2, 12, 64), (3, 5, 64), (2, 4, 80)])
-def test_attn_window(B, H, hd, window_version):
+def test_attn_window(B, H, hd):
     S = 14
     D = H * hd
     qkv = rnd(B, 64, 64, 3 * D, seed=29)
@@ -424,3 +414,123 @@ def test_nms_batched_small_bit_exact(per_class):
             ref = cand[opost.nms(rows[cand, :4], rows[cand, 4], 0.4)]
         assert int(keep_cnt[b]) == ref.shape[0]
         np.testing.assert_array_equal(keep_idx[b, :ref.shape[0]].cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------ round-2 additions: aliasing, benchmarked shapes, NaN
+@pytest.mark.parametrize("M,bn", [(700, 0), (700, 512), (40000, 0)])
+def test_gemm_inplace_residual_with_bf16_copy(M, bn):
+    """The last encoder block's call shape (engine.py, lin2): residual ALIASES the fp32 output (in-place update of the
+    residual stream) AND a bf16 copy is requested.  Both outputs must carry bias + residual (the bf16 copy of
+    the CTA-pair kernel lost the residual)."""
+    N, K = 768, 256
+    a, w = rnd(M, K, seed=60), rnd(N, K, seed=61, scale=K ** -0.5)
+    bias = rnd(N, seed=62, dtype=torch.float32)
+    x = rnd(M, N, seed=63, dtype=torch.float32, scale=3.0)
+    x0 = x.clone()
+    o16 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, bias, x, M, o16, x, 0, bn)
+    y = a.float() @ w.float().t() + bias + x0
+    assert (x - y).abs().max().item() < 5e-3
+    assert (o16.float() - y).abs().max().item() <= y.abs().max().item() * 2 ** -8 + 5e-3
+
+
+@pytest.mark.parametrize("M,N,K,act", [(131072, 2304, 768, 0), (131072, 3072, 768, 1), (131072, 768, 3072, 0),
+                                       (262144, 1280, 1280, 0), (262144, 256, 1280, 0)])
+def test_gemm_at_benchmarked_rows(M, N, K, act):
+    """The row counts the bench runs (batch 32: M = 131072; ViT-H batch 64: M = 262144): persistent tile schedulers and
+    32-bit index arithmetic only break at scale.  Reference = torch matmul on the same bf16 operands (fp32 result)."""
+    a, w = rnd(M, K, seed=64), rnd(N, K, seed=65, scale=K ** -0.5)
+    bias = rnd(N, seed=66, dtype=torch.float32)
+    res = rnd(M, N, seed=67, dtype=torch.float32) if act == 0 else None
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16 if act else torch.float32)
+    if act:
+        ops.gemm(a, w, bias, None, 0, out, None, act, 0)
+    else:
+        out.copy_(res)
+        ops.gemm(a, w, bias, out, M, None, out, 0, 0)  # in-place residual update (TMA reduce-add), as proj / lin2 do
+    for r0 in (0, M // 2 - 4096, M - 8192):  # check three 8192-row slabs incl. the last rows
+        sl = slice(r0, r0 + 8192)
+        y = a[sl].float() @ w.float().t() + bias
+        y = torch.nn.functional.gelu(y) if act else y + res[sl]
+        tol = 5e-2 if act else 5e-3
+        assert (out[sl].float() - y).abs().max().item() < tol, r0
+
+
+@pytest.mark.parametrize("B,H,hd", [(32, 12, 64), (64, 16, 80)])
+def test_attn_flash_global_relpos_at_benchmarked_batch(B, H, hd):
+    """Global attention at the batch sizes the bench runs (ViT-B batch 32, ViT-H batch 64); sampled (image, head) pairs
+    incl. the last ones are compared against fp32 torch."""
+    T, D = 4096, H * hd
+    qkv = rnd(B * T, 3 * D, seed=70)
+    rel_h, rel_w = rnd(127, hd, seed=71, scale=0.3), rnd(127, hd, seed=72, scale=0.3)
+    table = torch.zeros(256, hd, device=DEV, dtype=torch.bfloat16)
+    table[:127], table[128:255] = rel_h, rel_w
+    out = torch.zeros(B * T, D, device=DEV, dtype=torch.bfloat16)
+    scale = hd ** -0.5
+    ops.attn_flash(qkv, 0, qkv, D, qkv, 2 * D, table, out, B, H, T, T, hd, scale)
+    v3 = qkv.view(B, T, 3, H, hd)
+    for b, h in ((0, 0), (B // 2, H // 2), (B - 1, H - 1), (B - 1, 0), (7 % B, 5 % H)):
+        q, k, v = (v3[b, :, i, h][None, None] for i in range(3))
+        ref = ref_attention(q, k, v, scale, relpos_bias(q, rel_h, rel_w, 64))[0, 0]
+        got = out.view(B, T, H, hd)[b, :, h].float()
+        assert (got - ref).abs().max().item() < 2e-2, (b, h)
+
+
+@pytest.mark.parametrize("B,H,hd", [(32, 12, 64), (64, 16, 80)])
+def test_attn_window_at_benchmarked_batch(B, H, hd):
+    S, D = 14, H * hd
+    qkv = rnd(B, 64, 64, 3 * D, seed=73)
+    rel_h, rel_w = rnd(27, hd, seed=74, scale=0.3), rnd(27, hd, seed=75, scale=0.3)
+    table = torch.zeros(64, hd, device=DEV, dtype=torch.bfloat16)
+    table[:27], table[32:59] = rel_h, rel_w
+    out = torch.zeros(B, 64, 64, D, device=DEV, dtype=torch.bfloat16)
+    scale = hd ** -0.5
+    ops.attn_window(qkv, table, out, H, scale)
+    for b in (0, B // 2, B - 1):
+        xp = torch.nn.functional.pad(qkv[b:b + 1].float(), (0, 0, 0, 6, 0, 6))
+        win = xp.view(1, 5, S, 5, S, 3 * D).permute(0, 1, 3, 2, 4, 5).reshape(25, S * S, 3, H, hd).permute(2, 0, 3, 1, 4)
+        q, k, v = win[0], win[1], win[2]
+        o = ref_attention(q, k, v, scale, relpos_bias(q, rel_h, rel_w, S))
+        o = o.transpose(1, 2).reshape(1, 5, 5, S, S, D).permute(0, 1, 3, 2, 4, 5).reshape(70, 70, D)[:64, :64]
+        assert (out[b].float() - o).abs().max().item() < 2e-2, b
+
+
+def test_attn_flash_hfc_at_benchmarked_batch():
+    """HFC cross-attention shape (8 heads x 128) at batch 32; sampled (image, head) pairs vs fp32 torch."""
+    B, H, hd, T = 32, 8, 128, 4096
+    q = rnd(B * T, H * hd, seed=76)
+    kv = rnd(B * T, 2 * H * hd, seed=77)
+    out = torch.zeros(B * T, H * hd, device=DEV, dtype=torch.bfloat16)
+    scale = 1 / math.sqrt(hd)
+    ops.attn_flash(q, 0, kv, 0, kv, H * hd, None, out, B, H, T, T, hd, scale)
+    for b, h in ((0, 0), (B - 1, H - 1), (13, 3)):
+        qq = q.view(B, T, H, hd)[b, :, h][None, None]
+        kk = kv.view(B, T, 2, H, hd)[b, :, 0, h][None, None]
+        vv = kv.view(B, T, 2, H, hd)[b, :, 1, h][None, None]
+        ref = ref_attention(qq, kk, vv, scale)[0, 0]
+        assert (out.view(B, T, H, hd)[b, :, h].float() - ref).abs().max().item() < 2e-2, (b, h)
+
+
+def test_nan_scores_do_not_fault():
+    """NaN scores (NaN logits) must give a well-defined order (NaN first, torch.sort(descending) convention) and never an
+    out-of-bounds gather (colliding ranks left order slots unwritten)."""
+    n = 1500
+    b, s, _ = opost.make_nms_problem(n, seed=9)
+    s = s.copy()
+    s[[3, 700, 1499]] = np.nan
+    keep = _run_nms(b, s, None)
+    torch.cuda.synchronize()
+    assert keep.shape[0] > 0 and keep.min() >= 0 and keep.max() < n
+    s_ref = s.copy()
+    s_ref[[3, 700, 1499]] = [1e30, 1e29, 1e28]  # the same total order without NaN
+    np.testing.assert_array_equal(keep, opost.nms(b, s_ref, 0.4))
+    B, Q, K = 1, 300, 50
+    logits = torch.randn(B, Q, 8, device=DEV)
+    logits[0, 5, 2] = float("nan")
+    scores, labels = torch.zeros(B, K, device=DEV), torch.zeros(B, K, device=DEV, dtype=torch.int32)
+    query, ob = torch.zeros(B, K, device=DEV, dtype=torch.int32), torch.zeros(B, K, 4, device=DEV)
+    ops.sigmoid_topk(logits, torch.rand(B, Q, 4, device=DEV), torch.zeros(B, Q * 7, device=DEV),
+                     torch.zeros(B, Q * 7, device=DEV, dtype=torch.int32), scores, labels, query, ob, 7, K, 0)
+    torch.cuda.synchronize()
+    assert int(query[0, 0]) == 5 and int(labels[0, 0]) == 2
+    assert (query >= 0).all() and (query < Q).all()

@@ -92,7 +92,7 @@ def test_vit_b_vs_reference_golden(golden_dir):
     got = f[torch.from_numpy(sample_positions(f.numel(), "features")).to(DEV)].cpu().numpy()
     d = np.abs(got - g["features.samples"])
     print(f"[vit_b] features max-abs {d.max():.3e} mean-abs {d.mean():.3e} (|ref| max {np.abs(g['features.samples']).max():.2f})")
-    assert d.max() <= 1e-1 and d.mean() <= 1.2e-2
+    assert d.max() <= 5e-2 and d.mean() <= 6e-3  # the bf16 proxy of SURVEY.md section 0.7 (measured 1.9e-2 / 4.7e-3)
     # high-pass image vs the reference's FFT path
     h = mask.float().contiguous().view(-1)
     got = h[torch.from_numpy(sample_positions(h.numel(), "x_hfc")).to(DEV)].cpu().numpy()
@@ -129,10 +129,10 @@ def test_tiny_model_stage_parity_vs_oracle():
         assert d.max().item() <= tol_max, name
 
     cmp("x_hfc", hfc_img, otaps["x_hfc"], 2e-2)
-    cmp("after_hfc", taps["after_hfc"], otaps["after_hfc"], 1e-1)
-    cmp("block0", taps["block0"], otaps["block0"], 1.5e-1)
-    cmp("block1", taps["block1"], otaps["block1"], 2e-1)
-    cmp("features", feat.view(2, 4096, 256).transpose(1, 2), otaps["features"].flatten(2), 1e-1)
+    cmp("after_hfc", taps["after_hfc"], otaps["after_hfc"], 6e-2)  # (measured 3.1e-2 ... 3.9e-2 on |x| <= 10)
+    cmp("block0", taps["block0"], otaps["block0"], 6e-2)
+    cmp("block1", taps["block1"], otaps["block1"], 6e-2)
+    cmp("features", feat.view(2, 4096, 256).transpose(1, 2), otaps["features"].flatten(2), 6e-2)
     cmp("logits", out["pred_logits"], oout["pred_logits"], 2e-2)
     cmp("boxes", out["pred_boxes"], oout["pred_boxes"], 5e-3)
 
@@ -183,3 +183,97 @@ def test_cuda_graph_replay_matches_eager():
             n, k = int(counts[b]), int(keep_cnt[b])
             assert torch.equal(g_packed[b, :n], packed[b, :n])
             assert torch.equal(g_keep_idx[b, :k], keep_idx[b, :k])
+
+
+# ------------------------------------------------------------------ round 2: call orders the reference allows
+def _decode(model, emb):
+    return model.mask_decoder(image_embeddings=emb, image_pe=model.prompt_encoder.get_dense_pe(),
+                              sparse_prompt_embeddings=None, dense_prompt_embeddings=None, multimask_output=False,
+                              hfc_embed=None)
+
+
+def test_encode_a_encode_b_decode_a():
+    """The encoder output carries a token-major twin that lives in the engine workspace; a later encode overwrites that
+    workspace.  Decoding the FIRST embedding afterwards must still decode the first image (it decoded B)."""
+    model = build("vit_t", 51)
+    A, Bt = make_tiles(1, seed=2).to(DEV), make_tiles(1, seed=7).to(DEV)
+    with torch.no_grad():
+        ref = model(NestedTensor(A, None), None)
+        ref_l, ref_b = ref["pred_logits"].clone(), ref["pred_boxes"].clone()
+        emb_a = model.image_encoder(A, model.fft(A))
+        emb_b = model.image_encoder(Bt, model.fft(Bt))
+        out_a = _decode(model, emb_a)          # twin of emb_a is stale -> transpose path
+        la, ba = out_a["pred_logits"].clone(), out_a["pred_boxes"].clone()
+        out_b = _decode(model, emb_b)          # twin of emb_b is current
+        ref_bt = model(NestedTensor(Bt, None), None)
+    assert torch.equal(la, ref_l) and torch.equal(ba, ref_b)
+    assert torch.equal(out_b["pred_logits"], ref_bt["pred_logits"]) and torch.equal(out_b["pred_boxes"], ref_bt["pred_boxes"])
+    assert not torch.equal(la, out_b["pred_logits"])
+
+
+def test_inplace_edit_of_the_embedding_is_seen():
+    model = build("vit_t", 51)
+    A = make_tiles(1, seed=2).to(DEV)
+    with torch.no_grad():
+        emb = model.image_encoder(A, model.fft(A))
+        base = _decode(model, emb)["pred_logits"].clone()
+        emb.mul_(0.5)                                      # bumps emb._version: the workspace twin no longer describes it
+        got = _decode(model, emb)["pred_logits"].clone()
+        want = _decode(model, emb.clone())["pred_logits"]  # a clone has no twin: plain transpose path
+    assert torch.equal(got, want)
+    assert not torch.equal(got, base)
+
+
+def test_fft_a_fft_b_encode_a():
+    """MedSAM.fft leaves im2col rows for the encoder in the workspace; fft(A); fft(B); image_encoder(A, mask_A) must
+    not pick up B's rows, and an in-place edit of the mask must be honoured."""
+    model = build("vit_t", 51)
+    A, Bt = make_tiles(1, seed=2).to(DEV), make_tiles(1, seed=7).to(DEV)
+    with torch.no_grad():
+        want = model.image_encoder(A, model.fft(A)).clone()
+        mask_a = model.fft(A)
+        mask_b = model.fft(Bt)
+        got = model.image_encoder(A, mask_a).clone()
+        want_b = model.image_encoder(Bt, mask_b).clone()
+        mask_a2 = model.fft(A)
+        mask_a2.zero_()
+        got_zero = model.image_encoder(A, mask_a2).clone()
+        want_zero = model.image_encoder(A, torch.zeros_like(mask_a2)).clone()
+    assert torch.equal(got, want)
+    assert not torch.equal(got, want_b)
+    assert torch.equal(got_zero, want_zero) and not torch.equal(got_zero, want)
+
+
+# ------------------------------------------------------------------ round 2: parity at the benchmarked shapes
+def test_vit_b_batch32_matches_single_tile_and_oracle():
+    """The bench runs ViT-B at batch 32 (M = 131072 token rows: CTA-pair GEMMs, 6144-CTA attention grids).  Tile i of
+    the batch must equal the same tile run alone, and sampled tiles must meet the oracle gates."""
+    model = build("vit_b", 51)
+    tiles = make_tiles(32, seed=2)
+    with torch.no_grad():
+        out = model(NestedTensor(tiles.to(DEV), None), None)
+        L, Bx = out["pred_logits"].clone(), out["pred_boxes"].clone()
+        for i in (0, 13, 31):
+            o1 = model(NestedTensor(tiles[i:i + 1].to(DEV), None), None)
+            dl = (o1["pred_logits"][0] - L[i]).abs().max().item()
+            db = (o1["pred_boxes"][0] - Bx[i]).abs().max().item()
+            print(f"[vit_b b32 tile {i} vs alone] logits {dl:.2e} boxes {db:.2e}")
+            # different GEMM tilings (CTA-pair vs single-CTA kernel) accumulate in a different order: not bitwise
+            assert dl <= 4e-3 and db <= 1e-3, (i, dl, db)
+    sd = make_state_dict("vit_b", seed=0)
+    for i in (5, 31):
+        ref = om.forward(sd, "vit_b", tiles[i:i + 1])
+        check_outputs({"pred_logits": L[i:i + 1], "pred_boxes": Bx[i:i + 1]}, ref["pred_logits"].numpy(),
+                      ref["pred_boxes"].numpy(), f"vit_b b32 tile {i}")
+
+
+@pytest.mark.parametrize("model_type", ["vit_l", "vit_h"])
+def test_full_size_large_models_vs_oracle(model_type):
+    """One full-size ViT-L / ViT-H tile (24 / 32 blocks; head dim 64 / 80) against the fp32 CPU oracle."""
+    model = build(model_type, 51)
+    tiles = make_tiles(2, seed=2)
+    with torch.no_grad():
+        out = model(NestedTensor(tiles.to(DEV), None), None)
+    ref = om.forward(make_state_dict(model_type, seed=0), model_type, tiles[1:2])
+    check_outputs({"pred_logits": out["pred_logits"][1:2], "pred_boxes": out["pred_boxes"][1:2]},
+                  ref["pred_logits"].numpy(), ref["pred_boxes"].numpy(), model_type)

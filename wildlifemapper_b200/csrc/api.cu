@@ -1,4 +1,5 @@
 // C ABI (include/wm_b200.h): argument validation, TMA tensor-map construction, dispatch.  No torch types.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
@@ -54,44 +55,55 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// Per-device init-once state (a process may drive several GPUs: every entry point works on the caller's CURRENT device).
 struct DeviceState {
   int checked = 0;  // 0 unknown, 1 ok, -1 bad
   int num_sms = 0;
-  EncodeTiledFn encode = nullptr;
   std::string why;
 };
-DeviceState g_dev;
+constexpr int kMaxDevices = 64;
+DeviceState g_devs[kMaxDevices];
+EncodeTiledFn g_encode = nullptr;  // driver entry point (process-wide), set under g_mu
 std::mutex g_mu;
+thread_local int t_num_sms = 0;    // SM count of the device ensure_device() last validated on this thread
 
 int ensure_device() {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (g_dev.checked == 1) return WM_OK;
-  if (g_dev.checked == -1) return fail(WM_ERR_ARCH, "%s", g_dev.why.c_str());
   int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return fail(WM_ERR_ARCH, "no CUDA device");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceState& d = g_devs[dev];
+  if (d.checked == 1) {
+    t_num_sms = d.num_sms;
+    return WM_OK;
+  }
+  if (d.checked == -1) return fail(WM_ERR_ARCH, "%s", d.why.c_str());
   cudaDeviceProp prop;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
-    g_dev.why = "no CUDA device";
-    g_dev.checked = -1;
-    return fail(WM_ERR_ARCH, "%s", g_dev.why.c_str());
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    d.why = "no CUDA device";
+    d.checked = -1;
+    return fail(WM_ERR_ARCH, "%s", d.why.c_str());
   }
   if (prop.major != 10) {
     char b[128];
     snprintf(b, sizeof(b), "wm_b200 requires sm_100 (B200); found sm_%d%d -- there is no fallback path", prop.major,
              prop.minor);
-    g_dev.why = b;
-    g_dev.checked = -1;
-    return fail(WM_ERR_ARCH, "%s", g_dev.why.c_str());
+    d.why = b;
+    d.checked = -1;
+    return fail(WM_ERR_ARCH, "%s", d.why.c_str());
   }
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
-    g_dev.why = "cuTensorMapEncodeTiled not available from the driver";
-    g_dev.checked = -1;
-    return fail(WM_ERR_ARCH, "%s", g_dev.why.c_str());
+  if (g_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
+      d.why = "cuTensorMapEncodeTiled not available from the driver";
+      d.checked = -1;
+      return fail(WM_ERR_ARCH, "%s", d.why.c_str());
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  g_dev.encode = reinterpret_cast<EncodeTiledFn>(fn);
-  g_dev.num_sms = prop.multiProcessorCount;
-  g_dev.checked = 1;
+  d.num_sms = prop.multiProcessorCount;
+  d.checked = 1;
+  t_num_sms = d.num_sms;
   return WM_OK;
 }
 
@@ -111,7 +123,7 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, co
       gs[i - 1] = strides_bytes[i - 1];
     }
   }
-  CUresult r = g_dev.encode(m, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+  CUresult r = g_encode(m, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(WM_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
@@ -126,10 +138,9 @@ int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, u
   return make_map(m, ptr, 2, dims, strides, box, what);
 }
 
-int g_flash_version = 4;
-int g_flash_turns = 1;
-int g_gemm_pairs = 1;
-int g_window_version = 2;
+// A/B measurement knobs: atomics (set from any thread; every call reads each knob once)
+std::atomic<int> g_flash_version{4};
+std::atomic<int> g_gemm_pairs{1};
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -140,19 +151,16 @@ extern "C" {
 int wm_version(void) { return 100; }
 const char* wm_last_error(void) { return g_err.c_str(); }
 int wm_device_check(void) { return ensure_device(); }
-int wm_set_flash_version(int version);
+int wm_set_flash_version(int version) {
+  if (version != 4) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 4");
+  g_flash_version.store(version);
+  return WM_OK;
+}
 int wm_set_option(const char* name, int value) {
   const std::string n(name ? name : "");
   if (n == "flash_version") return wm_set_flash_version(value);
-  if (n == "flash_turns") { g_flash_turns = value != 0; return WM_OK; }
-  if (n == "gemm_pairs") { g_gemm_pairs = value != 0; return WM_OK; }
-  if (n == "window_version") { g_window_version = value == 1 ? 1 : 2; return WM_OK; }
+  if (n == "gemm_pairs") { g_gemm_pairs.store(value != 0); return WM_OK; }
   return fail(WM_ERR_SHAPE, "wm_set_option: unknown option '%s'", n.c_str());
-}
-int wm_set_flash_version(int version) {
-  if (version != 1 && version != 3 && version != 4 && version != 6) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 1, 3, 4 or 6");
-  g_flash_version = version;
-  return WM_OK;
 }
 
 int wm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
@@ -168,7 +176,7 @@ int wm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const f
   // kernel with a 128 x bn tile
   int bn = bn_hint;
   if (bn == 0) {
-    if (N % 256 == 0 && M >= 256 * (g_dev.num_sms / 2) && g_gemm_pairs) bn = 512;
+    if (N % 256 == 0 && M >= 256 * (t_num_sms / 2) && g_gemm_pairs.load()) bn = 512;
     else bn = (N >= 256) ? 256 : (N > 64 ? 128 : 64);
   }
   if (bn != 64 && bn != 128 && bn != 256 && bn != 512) return fail(WM_ERR_SHAPE, "wm_gemm_bf16: bn_hint must be 0/64/128/256/512");
@@ -187,8 +195,9 @@ int wm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const f
              (out_bf16 == nullptr || (aligned16(out_bf16) && ldc_bf16 % 8 == 0)) &&
              (out_f32 == nullptr || (aligned16(out_f32) && ldc_f32 % 4 == 0));
   // TMA-store epilogue: exactly one output, 16-byte aligned rows; bf16 stores are 64 columns wide (tiles of >= 128 columns)
-  p.res_inplace = residual != nullptr && residual == out_f32 && ldr == ldc_f32 && res_mod >= M;
+  // (with a second, bf16 output the residual has to be read: the TMA reduce-add only updates the fp32 copy)
   const bool dual = out_bf16 != nullptr && out_f32 != nullptr;
+  p.res_inplace = residual != nullptr && residual == out_f32 && ldr == ldc_f32 && res_mod >= M && !dual;
   p.tma_out = (p.vec_ok && N % 8 == 0 && N >= 64 && (out_f32 != nullptr || bn >= 128) && (!dual || bn == 512)) ? (dual ? 2 : 1) : 0;
   CUtensorMap tc16 = ta, tc32 = ta;
   if (p.tma_out) {
@@ -204,7 +213,7 @@ int wm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const f
       if (int rc = make_map(&tc32, out_f32, 2, dims, strides, box, "wm_gemm_bf16(out_f32)", CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return rc;
     }
   }
-  return check_launch(wm::gemm_dispatch(ta, tw, tc16, tc32, p, bn, g_dev.num_sms, (cudaStream_t)stream), "wm_gemm_bf16");
+  return check_launch(wm::gemm_dispatch(ta, tw, tc16, tc32, p, bn, t_num_sms, (cudaStream_t)stream), "wm_gemm_bf16");
 }
 
 int wm_conv3x3_nhwc_bf16(const void* X, const void* W, void* out_bf16, float* out_f32, int B, int C, int N,
@@ -227,7 +236,7 @@ int wm_conv3x3_nhwc_bf16(const void* X, const void* W, void* out_bf16, float* ou
   p.a_mode = 1; p.conv_C = C;
   p.vec_ok = (N % 4 == 0) && (out_bf16 == nullptr || aligned16(out_bf16)) && (out_f32 == nullptr || aligned16(out_f32));
   p.tma_out = 0; p.res_inplace = 0;
-  return check_launch(wm::gemm_dispatch(ta, tw, ta, ta, p, bn, g_dev.num_sms, (cudaStream_t)stream), "wm_conv3x3_nhwc_bf16");
+  return check_launch(wm::gemm_dispatch(ta, tw, ta, ta, p, bn, t_num_sms, (cudaStream_t)stream), "wm_conv3x3_nhwc_bf16");
 }
 
 int wm_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, const float* add,
@@ -269,6 +278,7 @@ int wm_hfc_finalize(const float* img, const float* low_t, void* patches_bf16, fl
 int wm_add_cast(const float* a, const float* b, int b_mod, void* out_bf16, int rows, int D, void* stream) {
   if (int rc = ensure_device()) return rc;
   if (!aligned16(a) || !aligned16(b) || !aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_add_cast: alignment");
+  if (a == nullptr && b == nullptr) return fail(WM_ERR_SHAPE, "wm_add_cast: a and b are both NULL");
   return check_launch(wm::add_cast_launch(a, b, b_mod > 0 ? b_mod : 1, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, D,
                                           (cudaStream_t)stream),
                       "wm_add_cast");
@@ -280,44 +290,33 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
                   int H, int Tq, int Tk, int hd, float scale, void* stream) {
   if (int rc = ensure_device()) return rc;
   if (B <= 0 || H <= 0 || (hd != 64 && hd != 80 && hd != 128)) return fail(WM_ERR_SHAPE, "wm_attn_flash: head dim must be 64, 80 or 128");
-  if (hd == 80 && (g_flash_version < 3 || (Tq % 256 != 0 && g_flash_version != 4 && g_flash_version != 6))) return fail(WM_ERR_SHAPE, "wm_attn_flash: head dim 80 needs the v3 / v4 kernel (Tq %% 256 == 0)");
-  const bool ragged = (Tq % 256 != 0) || (Tk % 128 != 0);  // only the v4 kernel masks ragged tiles (no rel-pos)
-  if (ragged && ((g_flash_version != 4 && g_flash_version != 6) || rel_table != nullptr || Tq < 1 || Tk < 1))
-    return fail(WM_ERR_SHAPE, "wm_attn_flash: Tq %% 256 != 0 or Tk %% 128 != 0 needs the v4 kernel without rel-pos");
-  if (!ragged && (Tq % 128 || Tk % 128 || Tk < 128)) return fail(WM_ERR_SHAPE, "wm_attn_flash: Tq, Tk must be multiples of 128");
+  const bool ragged = (Tq % 256 != 0) || (Tk % 128 != 0);  // ragged tiles are masked in the kernel (no rel-pos)
+  if (ragged && (rel_table != nullptr || Tq < 1 || Tk < 1))
+    return fail(WM_ERR_SHAPE, "wm_attn_flash: Tq %% 256 != 0 or Tk %% 128 != 0 is not supported together with rel-pos");
   if ((int64_t)B * Tq > q_rows || (int64_t)B * Tk > k_rows || (int64_t)B * Tk > v_rows) return fail(WM_ERR_SHAPE, "wm_attn_flash: rows");
   if (q_col0 + H * hd > q_width || k_col0 + H * hd > k_width || v_col0 + H * hd > v_width) return fail(WM_ERR_SHAPE, "wm_attn_flash: columns");
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || !aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_attn_flash: alignment");
   if (B > 65535 || H > 65535) return fail(WM_ERR_SHAPE, "wm_attn_flash: grid too large");
-  const bool v6 = (g_flash_version == 6);  // v4 everywhere except the three-tile kernel for head dim 64 + rel-pos
-  const bool v4 = (g_flash_version == 4) || v6;
-  const bool v3 = v4 || (g_flash_version == 3 && (Tq % 256 == 0));  // (v4 shares v3's tensor maps)
-  const uint32_t kv_box = 128;
   CUtensorMap tq, tk, tv, trel;
   if (int rc = make_map_2d(&tq, q, (uint64_t)q_rows, (uint64_t)q_width, (uint64_t)ldq, 128, "wm_attn_flash(q)")) return rc;
-  if (int rc = make_map_2d(&tk, k, (uint64_t)k_rows, (uint64_t)k_width, (uint64_t)ldk, kv_box, "wm_attn_flash(k)")) return rc;
-  if (int rc = make_map_2d(&tv, v, (uint64_t)v_rows, (uint64_t)v_width, (uint64_t)ldv, kv_box, "wm_attn_flash(v)")) return rc;
+  if (int rc = make_map_2d(&tk, k, (uint64_t)k_rows, (uint64_t)k_width, (uint64_t)ldk, 128, "wm_attn_flash(k)")) return rc;
+  if (int rc = make_map_2d(&tv, v, (uint64_t)v_rows, (uint64_t)v_width, (uint64_t)ldv, 128, "wm_attn_flash(v)")) return rc;
   trel = tq;
   if (rel_table != nullptr) {
-    if ((hd != 64 && !(hd == 80 && v3)) || Tq != 4096 || Tk != 4096)
-      return fail(WM_ERR_SHAPE, "wm_attn_flash: rel-pos needs hd 64 (or 80 on the v3 kernel) and 64x64 tokens");
-    if (int rc = make_map_2d(&trel, rel_table, 256, (uint64_t)hd, (uint64_t)hd, v3 ? 16 : 256, "wm_attn_flash(rel)")) return rc;
+    if ((hd != 64 && hd != 80) || Tq != 4096 || Tk != 4096)
+      return fail(WM_ERR_SHAPE, "wm_attn_flash: rel-pos needs head dim 64 or 80 and 64x64 tokens");
+    if (int rc = make_map_2d(&trel, rel_table, 256, (uint64_t)hd, (uint64_t)hd, 16, "wm_attn_flash(rel)")) return rc;
   }
   wm::FlashParams p{};
   p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.scale = scale;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldo = (int)ldo;
   p.use_relpos = rel_table != nullptr;
-  p.turns = g_flash_turns;
-  if (v6 && p.use_relpos && hd == 64) return check_launch(wm::flash6_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v6)");
-  if (v4) return check_launch(wm::flash4_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v4)");
-  if (v3) return check_launch(wm::flash3_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v3)");
-  return check_launch(wm::flash_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash");
+  return check_launch(wm::flash4_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v4)");
 }
 
 int wm_debug_flash_trace(uint64_t* host_out_3x64x4) {
-  const int rc = g_flash_version >= 4 ? wm::flash4_read_trace(reinterpret_cast<unsigned long long*>(host_out_3x64x4))
-                                      : wm::flash3_read_trace(reinterpret_cast<unsigned long long*>(host_out_3x64x4));
+  const int rc = wm::flash4_read_trace(reinterpret_cast<unsigned long long*>(host_out_3x64x4));
   if (rc != WM_OK)
     return fail(WM_ERR_ARCH, "wm_debug_flash_trace: only available in the diagnostics build (-DWM_F3_TRACE)");
   return WM_OK;
@@ -343,30 +342,22 @@ int wm_attn_window(const void* qkv, const void* rel_table, void* out_bf16, int B
   wm::WindowParams p{};
   p.B = B; p.H = H; p.scale = scale; p.D = D;
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  if (g_window_version == 2) {
-    // dense 14-wide boxes: a query half is 7 window rows x 14, K / V are the whole 14 x 14 window; zero padding of the
-    // 70x70 grid = TMA out-of-bounds fill on loads, the crop back to 64x64 = TMA bounds check on the output store
-    const uint32_t box_q[4] = {64, 14, 7, 1};
-    const uint32_t box_kv[4] = {64, 14, 14, 1};
-    const uint64_t odims[4] = {(uint64_t)D, 64, 64, (uint64_t)B};
-    const uint64_t ostrides[3] = {(uint64_t)D * 2, (uint64_t)D * 2 * 64, (uint64_t)D * 2 * 4096};
-    const uint64_t rdims[2] = {(uint64_t)hd, 64};
-    const uint64_t rstrides[1] = {(uint64_t)hd * 2};
-    const uint32_t rbox[2] = {64, 27};
-    if (int rc = make_map(&tq, qkv, 4, dims, strides, box_q, "wm_attn_window(q)")) return rc;
-    if (int rc = make_map(&tkv, qkv, 4, dims, strides, box_kv, "wm_attn_window(kv)")) return rc;
-    if (int rc = make_map(&trel, rel_table, 2, rdims, rstrides, rbox, "wm_attn_window(rel)")) return rc;
-    if (int rc = make_map(&tout, out_bf16, 4, odims, ostrides, box_q, "wm_attn_window(out)")) return rc;
-    if (hd == 80)  // ViT-H: same structure with two 64-column sub-tiles per operand row
-      return check_launch(wm::window3_dispatch(tq, tkv, trel, tout, p, g_dev.num_sms, (cudaStream_t)stream), "wm_attn_window(v2, hd 80)");
-    return check_launch(wm::window2_dispatch(tq, tkv, trel, tout, p, g_dev.num_sms, (cudaStream_t)stream), "wm_attn_window(v2)");
-  }
-  const uint32_t box_q[4] = {64, 16, 7, 1};
-  const uint32_t box_kv[4] = {64, 16, 14, 1};
+  // dense 14-wide boxes: a query half is 7 window rows x 14, K / V are the whole 14 x 14 window; zero padding of the
+  // 70x70 grid = TMA out-of-bounds fill on loads, the crop back to 64x64 = TMA bounds check on the output store
+  const uint32_t box_q[4] = {64, 14, 7, 1};
+  const uint32_t box_kv[4] = {64, 14, 14, 1};
+  const uint64_t odims[4] = {(uint64_t)D, 64, 64, (uint64_t)B};
+  const uint64_t ostrides[3] = {(uint64_t)D * 2, (uint64_t)D * 2 * 64, (uint64_t)D * 2 * 4096};
+  const uint64_t rdims[2] = {(uint64_t)hd, 64};
+  const uint64_t rstrides[1] = {(uint64_t)hd * 2};
+  const uint32_t rbox[2] = {64, 27};
   if (int rc = make_map(&tq, qkv, 4, dims, strides, box_q, "wm_attn_window(q)")) return rc;
   if (int rc = make_map(&tkv, qkv, 4, dims, strides, box_kv, "wm_attn_window(kv)")) return rc;
-  if (int rc = make_map_2d(&trel, rel_table, 64, (uint64_t)hd, (uint64_t)hd, 64, "wm_attn_window(rel)")) return rc;
-  return check_launch(wm::window_dispatch(tq, tkv, trel, p, hd, (cudaStream_t)stream), "wm_attn_window");
+  if (int rc = make_map(&trel, rel_table, 2, rdims, rstrides, rbox, "wm_attn_window(rel)")) return rc;
+  if (int rc = make_map(&tout, out_bf16, 4, odims, ostrides, box_q, "wm_attn_window(out)")) return rc;
+  if (hd == 80)  // ViT-H: same structure with two 64-column sub-tiles per operand row
+    return check_launch(wm::window3_dispatch(tq, tkv, trel, tout, p, t_num_sms, (cudaStream_t)stream), "wm_attn_window(hd 80)");
+  return check_launch(wm::window2_dispatch(tq, tkv, trel, tout, p, t_num_sms, (cudaStream_t)stream), "wm_attn_window");
 }
 
 int wm_attn_small(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out_bf16,

@@ -586,13 +586,8 @@ template <int HD, bool RELPOS>
 static int launch_flash4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                          const FlashParams& p, cudaStream_t st) {
   using Cfg = Flash4Cfg<HD, RELPOS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(flash4_kernel<HD, RELPOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
-        cudaSuccess)
-      return WM_ERR_CUDA;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_smem_attr(flash4_kernel<HD, RELPOS>, Cfg::SMEM_BYTES, attr_done)) return rc;
   dim3 grid((p.Tq + 255) / 256, p.H, p.B);
   flash4_kernel<HD, RELPOS><<<grid, F4_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, trel, p);
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;

@@ -450,12 +450,8 @@ window2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 // tout: box (64, 14, 7, 1) over out [B,64,64,D]
 int window2_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const CUtensorMap& tout,
                      const WindowParams& p, int num_sms, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(window2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM_BYTES) != cudaSuccess)
-      return WM_ERR_CUDA;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_smem_attr(window2_kernel, W2_SMEM_BYTES, attr_done)) return rc;
   const int items = p.B * 25 * p.H;
   const int grid = items < num_sms ? items : num_sms;
   window2_kernel<<<grid, W2_THREADS, W2_SMEM_BYTES, st>>>(tq, tkv, trel, tout, p);

@@ -459,12 +459,8 @@ window3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 // tout: box (64, 14, 7, 1) over out [B,64,64,D]
 int window3_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const CUtensorMap& tout,
                      const WindowParams& p, int num_sms, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(window3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W3_SMEM_BYTES) != cudaSuccess)
-      return WM_ERR_CUDA;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_smem_attr(window3_kernel, W3_SMEM_BYTES, attr_done)) return rc;
   const int items = p.B * 25 * p.H;
   const int grid = items < num_sms ? items : num_sms;
   window3_kernel<<<grid, W3_THREADS, W3_SMEM_BYTES, st>>>(tq, tkv, trel, tout, p);

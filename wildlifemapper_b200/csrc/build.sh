@@ -8,7 +8,8 @@ BUILD=${WM_BUILD_DIR:-build}
 LIBNAME=${WM_LIB_NAME:-libwm_b200.so}
 mkdir -p $BUILD
 pids=()
-for f in gemm attn_flash attn_flash3 attn_flash4 attn_flash6 attn_window attn_window2 attn_window3 elementwise postprocess frontend api; do
+SRCS="gemm attn_flash4 attn_window2 attn_window3 elementwise postprocess frontend api"
+for f in $SRCS; do
   if [ ! -f $BUILD/$f.o ] || [ $f.cu -nt $BUILD/$f.o ] || [ common.cuh -nt $BUILD/$f.o ] || [ wm_internal.h -nt $BUILD/$f.o ] || [ ../../include/wm_b200.h -nt $BUILD/$f.o ]; then
     $NVCC $FLAGS -Xptxas -v -c $f.cu -o $BUILD/$f.o > $BUILD/$f.log 2>&1 &
     pids+=($!)
@@ -17,5 +18,5 @@ done
 rc=0
 for p in "${pids[@]:-}"; do [ -z "$p" ] || wait $p || rc=1; done
 if [ $rc -ne 0 ]; then cat $BUILD/*.log | grep -E "error|Error" -B2 -A6 | head -80; exit 1; fi
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../$LIBNAME $BUILD/gemm.o $BUILD/attn_flash.o $BUILD/attn_flash3.o $BUILD/attn_flash4.o $BUILD/attn_flash6.o $BUILD/attn_window.o $BUILD/attn_window2.o $BUILD/attn_window3.o $BUILD/elementwise.o $BUILD/postprocess.o $BUILD/frontend.o $BUILD/api.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../$LIBNAME $(for f in $SRCS; do echo $BUILD/$f.o; done) -lcudart
 echo "built $(cd .. && pwd)/$LIBNAME"

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256) add_cast_kernel(const float* __restrict__
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= (size_t)rows * D4) return;
   const int row = (int)(i / D4), c4 = (int)(i % D4);
-  float4 v = __ldg(reinterpret_cast<const float4*>(a) + i);
+  float4 v = a ? __ldg(reinterpret_cast<const float4*>(a) + i) : make_float4(0.f, 0.f, 0.f, 0.f);  // a == null: broadcast-cast of b
   if (b) {
     const float4 w = __ldg(reinterpret_cast<const float4*>(b) + (size_t)(row % b_mod) * D4 + c4);
     v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;

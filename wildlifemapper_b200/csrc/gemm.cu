@@ -611,13 +611,8 @@ template <int ACT, int FAST>
 static int launch_gemm2_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc16, const CUtensorMap& tc32,
                                 const GemmParams& p, int num_sms, cudaStream_t st) {
   using Cfg = Gemm2Cfg;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm2_bf16_kernel<ACT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
-        cudaSuccess)
-      return WM_ERR_CUDA;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_smem_attr(gemm2_bf16_kernel<ACT, FAST>, Cfg::SMEM_BYTES, attr_done)) return rc;
   const int tiles = ((p.M + 255) / 256) * (p.N / 256);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
@@ -637,13 +632,8 @@ template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc16, const CUtensorMap& tc32,
                        const GemmParams& p, int num_sms, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
-        cudaSuccess)
-      return WM_ERR_CUDA;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_smem_attr(gemm_bf16_kernel<BN>, Cfg::SMEM_BYTES, attr_done)) return rc;
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(ta, tw, tc16, tc32, p);

@@ -90,21 +90,28 @@ int postprocess_launch(const float* in, const float* boxes, const long long* siz
 
 // ------------------------------------------------------------------ stable descending rank (exact argsort, O(n^2))
 // rank[i] = #{ j : s[j] > s[i]  or  (s[j] == s[i] and j < i) };  order[rank[i]] = i.
+// The comparison runs on an integer key that orders exactly like the floats (-0 == +0) and puts every NaN first (the
+// torch.sort(descending=True) convention), so the ranks are a permutation for ANY input and order[] is fully written.
+__device__ __forceinline__ int rank_key(float f) {
+  if (f != f) return 0x7fffffff;
+  const int b = __float_as_int(f + 0.0f);  // -0 -> +0
+  return b >= 0 ? b : (b ^ 0x7fffffff);
+}
 __global__ void __launch_bounds__(256) rank_desc_kernel(const float* __restrict__ s, int n, int* __restrict__ order,
                                                         size_t batch_stride_s, size_t batch_stride_o) {
-  __shared__ float tile[1024];
+  __shared__ int tile[1024];
   const float* sb = s + blockIdx.y * batch_stride_s;
   int* ob = order + blockIdx.y * batch_stride_o;
   const int i = blockIdx.x * 256 + threadIdx.x;
-  const float si = i < n ? sb[i] : 0.f;
+  const int si = i < n ? rank_key(sb[i]) : 0;
   int rank = 0;
   for (int j0 = 0; j0 < n; j0 += 1024) {
     __syncthreads();
-    for (int t = threadIdx.x; t < 1024; t += 256) tile[t] = (j0 + t < n) ? sb[j0 + t] : -INFINITY;
+    for (int t = threadIdx.x; t < 1024; t += 256) tile[t] = (j0 + t < n) ? rank_key(sb[j0 + t]) : (int)0x80000000;
     __syncthreads();
     const int lim = min(1024, n - j0);
     for (int t = 0; t < lim; ++t) {
-      const float sj = tile[t];
+      const int sj = tile[t];
       rank += (sj > si) || (sj == si && (j0 + t) < i);
     }
   }

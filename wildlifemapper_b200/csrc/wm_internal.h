@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #define WM_OK 0
 #define WM_ERR_SHAPE (-1)
 #define WM_ERR_ALIGN (-2)
@@ -12,6 +14,19 @@
 #define WM_ERR_CUDA (-4)
 
 namespace wm {
+
+// cudaFuncSetAttribute is per DEVICE: one bit per device ordinal records where the dynamic shared-memory limit of a
+// kernel has been raised (a process may drive several GPUs; the C ABI launches on the caller's current device).
+template <typename Kernel>
+inline int ensure_smem_attr(Kernel kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return WM_ERR_CUDA;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return WM_OK;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return WM_ERR_CUDA;
+  done.fetch_or(bit, std::memory_order_release);
+  return WM_OK;
+}
 
 struct GemmParams {
   int M, N, K;
@@ -41,20 +56,10 @@ struct FlashParams {
   int q_col0, k_col0, v_col0;  // first column of head 0 inside the q / k / v tensor maps
   __nv_bfloat16* out;
   int ldo;
-  int turns;       // v3: the two softmax warpgroups take turns on the MUFU (A/B knob "flash_turns")
   int use_relpos;  // global 64x64 grid decomposed rel-pos; tables via tmap_rel ([256, HD]: rows 0..126 Rh, 128..254 Rw)
 };
-int flash_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
-                   const FlashParams& p, int hd, cudaStream_t st);
-
-int flash3_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
-                    const FlashParams& p, int hd, cudaStream_t st);
-
 int flash4_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                     const FlashParams& p, int hd, cudaStream_t st);
-int flash6_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
-                    const FlashParams& p, int hd, cudaStream_t st);
-int flash3_read_trace(unsigned long long* host_out);
 int flash4_read_trace(unsigned long long* host_out);
 int window2_read_trace(unsigned long long* host_out);  // diagnostics build (-DWM_F3_TRACE) only
 
@@ -64,8 +69,6 @@ struct WindowParams {
   int D;        // embedding dim (q at col h*64, k at D + h*64, v at 2D + h*64 in the [B,64,64,3D] qkv tensor)
   __nv_bfloat16* out;  // [B,64,64,D]
 };
-int window_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const WindowParams& p, int hd,
-                    cudaStream_t st);
 int window2_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const CUtensorMap& tout,
                      const WindowParams& p, int num_sms, cudaStream_t st);
 int window3_dispatch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& trel, const CUtensorMap& tout,

@@ -38,3 +38,19 @@ def gather_detections(packed: torch.Tensor, counts: torch.Tensor, keep_idx: Opti
         return out
 
     return ag(packed), ag(counts), ag(keep_idx), ag(keep_cnt)
+
+
+def gather_buffer(buf, out_flat: Optional[torch.Tensor] = None, group=None):
+    """ONE all-gather of a ``postprocess.DetectionBuffer`` (all four detection tensors travel in one flat buffer).
+    Capturable in a CUDA graph (fixed addresses when ``out_flat`` is given).  Returns the gathered flat buffer
+    [world * n]; ``DetectionBuffer.split`` turns it into the four tensors."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return buf.flat
+    world = dist.get_world_size(group)
+    if out_flat is None:
+        out_flat = torch.empty(world * buf.flat.numel(), device=buf.flat.device, dtype=buf.flat.dtype)
+    if buf.flat.is_cuda:
+        dist.all_gather_into_tensor(out_flat, buf.flat, group=group)
+    else:
+        dist.all_gather(list(out_flat.chunk(world, dim=0)), buf.flat, group=group)
+    return out_flat

@@ -86,6 +86,10 @@ class EncoderEngine:
         self.ws = _Workspace(self.device)
         self.w: Dict[str, torch.Tensor] = {}
         self.launches = 0
+        # generation counters of the workspaces whose views leave the engine (validity tokens of the aliases the drop-in
+        # modules hang on API-visible tensors, see modeling/common.py::attach_twin): im2col rows / encoder features
+        self.gen_rows = 0
+        self.gen_feat = 0
 
     # ------------------------------------------------------------------ weight preparation
     def prepare(self, sd: Dict[str, torch.Tensor]) -> None:
@@ -151,6 +155,7 @@ class EncoderEngine:
         """E0 (+ im2col for E1/E2). Returns (patch rows bf16 [M,768], hfc rows bf16 [M,256], hfc image or None)."""
         B = img.shape[0]
         ws, w = self.ws, self.w
+        self.gen_rows += 1
         a_patch = ws.get("a_patch", (B * NTOK, 768), torch.bfloat16)
         gray = ws.get("gray", (B * 1024, 1024), torch.bfloat16)
         ops.patchify(img, a_patch, gray)
@@ -166,9 +171,22 @@ class EncoderEngine:
         self.launches += 5
         return a_patch, a_hfc, hfc_img
 
+    def patch_rows(self, img: torch.Tensor, hfc_img: torch.Tensor):
+        """im2col rows of a tile batch and of a caller-supplied high-pass image (ImageEncoderViT.forward called with an
+        x_hfc that did not come from MedSAM.fft in the same pass)."""
+        B = img.shape[0]
+        self.gen_rows += 1
+        a_patch = self.ws.get("a_patch", (B * NTOK, 768), torch.bfloat16)
+        ops.patchify(img, a_patch, None)
+        a_hfc = self.ws.get("a_hfc", (B * NTOK, 256), torch.bfloat16)
+        ops.patchify(hfc_img, a_hfc, None)
+        self.launches += 2
+        return a_patch, a_hfc
+
     def encode(self, a_patch: torch.Tensor, a_hfc: torch.Tensor, B: int, taps: Optional[dict] = None):
         """E1..E12 on im2col rows. Returns NHWC features: (fp32 [M,256], bf16 [M,256])."""
         D, H, M = self.D, self.H, B * NTOK
+        self.gen_feat += 1
         ws, w = self.ws, self.w
         bf, f32 = torch.bfloat16, torch.float32
         n0 = self.launches
@@ -356,9 +374,7 @@ class DecoderEngine:
         keysb = ws.get("keysb", (MK, 256), bf)
         keyspe = ws.get("keyspe", (MK, 256), bf)
         Y = ws.get("Y", (MQ, 256), f32)
-        zero = ws.get("zeroX", (MQ, 256), f32)
-        zero.zero_()
-        ops.add_cast(zero, tokens, tmod, Xb)  # queries = point_embedding (bf16 operand copy)
+        ops.add_cast(None, tokens, tmod, Xb)  # queries = point_embedding (bf16 operand copy, batch-broadcast)
         ops.add_cast(feat, None, 0, keysb)
         ops.add_cast(feat, pe, pmod, keyspe)
         keys_f32 = feat

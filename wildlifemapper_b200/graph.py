@@ -22,7 +22,8 @@ from . import postprocess as pp
 
 class GraphedDetector:
     def __init__(self, model, batch: int, target_size=(1024, 1024), conf_thr: float = 0.05, nms_score_thr: float = 0.5,
-                 iou_thr: float = 0.4, warmup: int = 2, device: Optional[torch.device] = None):
+                 iou_thr: float = 0.4, warmup: int = 2, device: Optional[torch.device] = None, per_class: bool = False,
+                 gather: bool = False):
         from segment_anything.utils.misc import NestedTensor  # the drop-in package (same container the callers use)
         self._nested = NestedTensor
         self.model = model
@@ -33,6 +34,18 @@ class GraphedDetector:
         self.static_in = torch.zeros(batch, 3, 1024, 1024, device=dev, dtype=torch.float32)
         self.sizes = torch.tensor([list(target_size)] * batch, device=dev, dtype=torch.int64)
         self._thr = (float(conf_thr), float(nms_score_thr), float(iou_thr))
+        self._per_class = bool(per_class)
+        Q = model.mask_decoder.num_mask_tokens
+        self.buffer = pp.DetectionBuffer(batch, Q, dev)  # the four outputs in one flat buffer (one all-gather)
+        # gather=True (torch.distributed initialised, world > 1): the NCCL all-gather of the detections is captured in
+        # the graph right behind the NMS, so a replay is ONE launch including the exchange
+        self.gathered = None
+        self._world = 1
+        if gather:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                self._world = dist.get_world_size()
+                self.gathered = torch.zeros(self._world * self.buffer.flat.numel(), device=dev, dtype=torch.float32)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():
@@ -47,9 +60,20 @@ class GraphedDetector:
     def _step(self):
         conf, score, iou = self._thr
         out = self.model(self._nested(self.static_in, None), None)
-        packed, _labels, _query, counts = pp.postprocess_packed(out["pred_logits"], out["pred_boxes"], self.sizes, conf)
-        keep_idx, keep_cnt = pp.nms_packed(packed, counts, score_thr=score, iou_threshold=iou)
+        packed, _labels, _query, counts = pp.postprocess_packed(out["pred_logits"], out["pred_boxes"], self.sizes, conf,
+                                                                out=self.buffer)
+        keep_idx, keep_cnt = pp.nms_packed(packed, counts, score_thr=score, iou_threshold=iou,
+                                           per_class=self._per_class, out=self.buffer)
+        if self.gathered is not None:
+            from .dist import gather_buffer
+            gather_buffer(self.buffer, self.gathered)
         return packed, counts, keep_idx, keep_cnt
+
+    def gathered_outputs(self):
+        """(packed [world*B,Q,6], counts, keep_idx, keep_cnt) of ALL ranks after a replay (gather=True)."""
+        if self.gathered is None:
+            return self.outputs
+        return pp.DetectionBuffer.split(self.gathered, self._world, self.buffer.B, self.buffer.Q)
 
     def replay(self):
         """Run the captured step on whatever ``static_in`` holds."""

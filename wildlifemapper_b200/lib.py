@@ -66,8 +66,7 @@ def load() -> C.CDLL:
         fn.argtypes = argtypes
         fn.restype = C.c_char_p if name == "wm_last_error" else C.c_int
     _lib = lib
-    for env, opt in (("WM_FLASH_VERSION", b"flash_version"), ("WM_FLASH_TURNS", b"flash_turns"),
-                     ("WM_GEMM_PAIRS", b"gemm_pairs"), ("WM_WINDOW_VERSION", b"window_version")):
+    for env, opt in (("WM_FLASH_VERSION", b"flash_version"), ("WM_GEMM_PAIRS", b"gemm_pairs")):
         if os.environ.get(env):  # measurement knobs, see include/wm_b200.h
             lib.wm_set_option(opt, int(os.environ[env]))
     return lib

@@ -34,10 +34,24 @@ def _chk(t: Optional[torch.Tensor], dtype, name: str, inner_contig: bool = True)
         raise _lib.WmError(f"{name}: innermost dimension must be contiguous")
 
 
+def _on_tensor_device(fn):
+    """Launch on the device (and that device's current stream) of the op's tensors, not on whatever device happens to be
+    current: the C ABI works on the caller's current device."""
+    def run(*args):
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda and a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args)
+                break
+        return fn(*args)
+    return run
+
+
 def _define(schema: str, fn) -> None:
     name = schema.split("(", 1)[0]
     _LIBRARY.define(schema)
-    _LIBRARY.impl(name, fn, "CUDA")
+    _LIBRARY.impl(name, _on_tensor_device(fn), "CUDA")
 
 
 # ------------------------------------------------------------------ GEMM family
@@ -132,12 +146,12 @@ _define("hfc_finalize(Tensor img, Tensor low_t, Tensor(a!) patches, Tensor(b!)? 
 
 def _add_cast(a, b, b_mod, out):
     _chk(a, torch.float32, "add_cast.a"); _chk(b, torch.float32, "add_cast.b"); _chk(out, torch.bfloat16, "add_cast.out")
-    assert a.is_contiguous() and out.is_contiguous() and out.numel() == a.numel()
-    D = a.shape[-1]
-    _lib.call("wm_add_cast", a.data_ptr(), _ptr(b), int(b_mod), out.data_ptr(), a.numel() // D, D, _stream())
+    assert out.is_contiguous() and (a is None or (a.is_contiguous() and out.numel() == a.numel())) and (a is not None or b is not None)
+    D = out.shape[-1]
+    _lib.call("wm_add_cast", _ptr(a), _ptr(b), int(b_mod), out.data_ptr(), out.numel() // D, D, _stream())
 
 
-_define("add_cast(Tensor a, Tensor? b, int b_mod, Tensor(a!) out) -> ()", _add_cast)
+_define("add_cast(Tensor? a, Tensor? b, int b_mod, Tensor(a!) out) -> ()", _add_cast)
 
 
 # ------------------------------------------------------------------ attention

@@ -5,7 +5,7 @@ from typing import Optional, Type
 import torch
 from torch import nn
 
-from .common import _MSG, params_version, require_inference
+from .common import _MSG, params_version, require_inference, twin_of
 
 
 class MLP(nn.Module):
@@ -57,9 +57,9 @@ class MaskDecoder(nn.Module):
         Q = self.num_mask_tokens
 
         def to_tokens(t: torch.Tensor, name: str) -> torch.Tensor:
-            nhwc = getattr(t, "_wm_nhwc", None)
-            if nhwc is not None:
-                return nhwc[0]
+            rows = twin_of(t)  # token-major twin left by the encoder / get_dense_pe, if still valid
+            if rows is not None:
+                return rows
             out = eng.ws.get(name, (t.shape[0] * 4096, 256), torch.float32)
             ops.transpose(t.contiguous().float().view(t.shape[0], 256, 4096), out.view(t.shape[0], 4096, 256))
             return out

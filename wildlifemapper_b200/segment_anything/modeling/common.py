@@ -26,6 +26,26 @@ def params_version(mod: nn.Module):
     return tuple((t.data_ptr(), t._version) for t in list(mod.parameters()) + list(mod.buffers()))
 
 
+def attach_twin(t: torch.Tensor, rows: torch.Tensor, engine=None, gen_attr: str = "") -> None:
+    """Hang the token-major twin ``rows`` ([*,4096,C] rows of the NCHW tensor ``t``) on ``t`` so that the next stage can
+    skip a transpose round trip.  The twin may live in an engine WORKSPACE that later calls overwrite, and ``t`` may be
+    edited in place by the caller, so the attachment carries a validity token: the engine's generation counter for that
+    workspace and ``t._version``.  ``twin_of`` returns the twin only while both still match (the reference allows any
+    call order: encode A, encode B, decode A must decode A)."""
+    gen = getattr(engine, gen_attr) if engine is not None else None
+    t._wm_twin = (rows, engine, gen_attr, gen, t._version)
+
+
+def twin_of(t: torch.Tensor):
+    tw = getattr(t, "_wm_twin", None)
+    if tw is None:
+        return None
+    rows, engine, gen_attr, gen, version = tw
+    if t._version != version or (engine is not None and getattr(engine, gen_attr) != gen):
+        return None
+    return rows
+
+
 class MLPBlock(nn.Module):
     def __init__(self, embedding_dim: int, mlp_dim: int, act: Type[nn.Module] = nn.GELU) -> None:
         super().__init__()

@@ -9,9 +9,8 @@ import torch
 import torch.nn as nn
 
 from wildlifemapper_b200.engine import EncoderEngine
-from wildlifemapper_b200.ops import ops
 
-from .common import LayerNorm2d, MLPBlock, _MSG, params_version, require_inference
+from .common import LayerNorm2d, MLPBlock, _MSG, attach_twin, params_version, require_inference
 
 
 class PatchEmbed(nn.Module):
@@ -151,18 +150,33 @@ class ImageEncoderViT(nn.Module):
                             "image_encoder.py:128)")
         require_inference(self, x, x_hfc)
         eng = self.engine()
+        x_in = x
         x = x.contiguous().float()
         B = x.shape[0]
+        a_patch = a_hfc = None
         cached = getattr(x_hfc, "_wm_rows", None)
-        if cached is not None and cached[0] == (x.data_ptr(), x._version):
-            a_patch, a_hfc = cached[1], cached[2]  # produced by MedSAM.fft in the same pass over the tile
-        else:
-            a_patch = eng.ws.get("a_patch", (B * 4096, 768), torch.bfloat16)
-            ops.patchify(x, a_patch, None)
-            a_hfc = eng.ws.get("a_hfc", (B * 4096, 256), torch.bfloat16)
-            ops.patchify(x_hfc.contiguous().float(), a_hfc, None)
-            eng.launches += 2
-        feat, featb = eng.encode(a_patch, a_hfc, B)
+        if cached is not None:
+            # im2col rows produced by MedSAM.fft in the same pass over the tile: valid only while (a) it is the very same
+            # image tensor, unmodified, (b) the mask was not edited in place, (c) no later call overwrote the workspace
+            ref, x_ver, hfc_ver, c_eng, gen, rows_p, rows_h = cached
+            if ref() is x_in and x_in._version == x_ver and x_hfc._version == hfc_ver and c_eng is eng \
+                    and eng.gen_rows == gen:
+                a_patch, a_hfc = rows_p, rows_h
+        if a_patch is None:
+            a_patch, a_hfc = eng.patch_rows(x, x_hfc.contiguous().float())
+        return self._encode_rows(eng, a_patch, a_hfc, B)
+
+    def _encode_rows(self, eng: EncoderEngine, a_patch, a_hfc, B: int) -> torch.Tensor:
+        feat, _featb = eng.encode(a_patch, a_hfc, B)
         out = eng.to_nchw(feat, B)
-        out._wm_nhwc = (feat, featb)  # token-major copies for the decoder (avoids a transpose round trip)
+        attach_twin(out, feat, eng, "gen_feat")  # token-major copy for the decoder (avoids a transpose round trip)
         return out
+
+    def forward_tiles(self, x: torch.Tensor) -> torch.Tensor:
+        """MedSAM.forward's fused route: fft high-pass + encoder in one pass over the tiles (the high-pass image itself is
+        never written: only its im2col rows are needed)."""
+        require_inference(self, x)
+        eng = self.engine()
+        x = x.contiguous().float()
+        a_patch, a_hfc, _ = eng.highpass(x, want_image=False)
+        return self._encode_rows(eng, a_patch, a_hfc, x.shape[0])

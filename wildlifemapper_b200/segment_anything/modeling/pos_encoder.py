@@ -8,6 +8,8 @@ from torch import nn
 
 from wildlifemapper_b200.engine import DecoderEngine
 
+from .common import attach_twin
+
 
 class PositionEmbeddingRandom(nn.Module):
     def __init__(self, num_pos_feats: int = 64, scale: Optional[float] = None) -> None:
@@ -30,7 +32,7 @@ class PositionEmbeddingRandom(nn.Module):
             raise NotImplementedError("dense PE is specialised to the 64x64 embedding grid")
         tok = self.dense_tokens()
         chw = tok.t().contiguous().view(tok.shape[1], 64, 64)
-        chw._wm_nhwc = (tok, None)
+        attach_twin(chw, tok)
         return chw
 
 
@@ -48,6 +50,6 @@ class PromptEncoder(nn.Module):
         tok = self.pe_layer.dense_tokens()
         if self._pe is None or self._pe[0] is not tok:
             pe = tok.t().contiguous().view(1, tok.shape[1], 64, 64)
-            pe._wm_nhwc = (tok, None)
+            attach_twin(pe, tok)
             self._pe = (tok, pe)
         return self._pe[1]

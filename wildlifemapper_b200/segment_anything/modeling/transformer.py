@@ -7,7 +7,7 @@ from torch import Tensor, nn
 
 from wildlifemapper_b200.engine import DecoderEngine
 
-from .common import MLPBlock, _MSG, params_version, require_inference
+from .common import MLPBlock, _MSG, params_version, require_inference, twin_of
 
 
 class Attention(nn.Module):
@@ -89,9 +89,9 @@ class TwoWayTransformer(nn.Module):
         Q = point_embedding.shape[1]
 
         def to_tokens(t: Tensor, name: str) -> Tensor:
-            nhwc = getattr(t, "_wm_nhwc", None)
-            if nhwc is not None:
-                return nhwc[0]
+            rows = twin_of(t)  # token-major twin left by the encoder / get_dense_pe, if still valid
+            if rows is not None:
+                return rows
             out = eng.ws.get(name, (t.shape[0] * 4096, 256), torch.float32)
             ops.transpose(t.contiguous().float().view(t.shape[0], 256, 4096), out.view(t.shape[0], 4096, 256))
             return out

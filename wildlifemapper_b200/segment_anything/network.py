@@ -1,5 +1,7 @@
 """MedSAM wrapper with the reference's constructor, freezing policy and ``forward(image, box)`` signature
 (reference ``segment_anything/network.py``)."""
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -30,18 +32,19 @@ class MedSAM(nn.Module):
             raise NotImplementedError("the low-pass operator is built for the reference's rate=0.125")
         x = img.tensors if hasattr(img, "tensors") else img
         require_inference(self, x)
-        x = x.contiguous().float()
+        xc = x.contiguous().float()
         eng = self.image_encoder.engine()
-        a_patch, a_hfc, hfc_img = eng.highpass(x, want_image=True)
-        hfc_img._wm_rows = ((x.data_ptr(), x._version), a_patch, a_hfc)
+        a_patch, a_hfc, hfc_img = eng.highpass(xc, want_image=True)
+        if xc is x:  # (a converted temporary could be freed and its address reused: never key a cache on it)
+            hfc_img._wm_rows = (weakref.ref(x), x._version, hfc_img._version, eng, eng.gen_rows, a_patch, a_hfc)
         return hfc_img
 
     def forward(self, image, box):
         """image: NestedTensor (``.tensors`` [B,3,1024,1024] fp32 on the GPU); ``box`` is accepted and ignored like
         in the reference (network.py:69-78).  Returns {'pred_logits': [B,Q,8], 'pred_boxes': [B,Q,4]} fp32."""
-        mask = self.fft(image)
         x = image.tensors if hasattr(image, "tensors") else image
-        image_embedding = self.image_encoder(x.contiguous().float(), mask)
+        # = image_encoder(x, self.fft(image)) (network.py:80-81) without materialising the fp32 high-pass image
+        image_embedding = self.image_encoder.forward_tiles(x)
         return self.mask_decoder(
             image_embeddings=image_embedding,
             image_pe=self.prompt_encoder.get_dense_pe(),

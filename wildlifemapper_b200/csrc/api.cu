@@ -139,7 +139,7 @@ int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, u
 }
 
 // A/B measurement knobs: atomics (set from any thread; every call reads each knob once)
-std::atomic<int> g_flash_version{4};
+std::atomic<int> g_flash_version{7};
 std::atomic<int> g_gemm_pairs{1};
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -152,7 +152,7 @@ int wm_version(void) { return 100; }
 const char* wm_last_error(void) { return g_err.c_str(); }
 int wm_device_check(void) { return ensure_device(); }
 int wm_set_flash_version(int version) {
-  if (version != 4) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 4");
+  if (version != 4 && version != 7) return fail(WM_ERR_SHAPE, "wm_set_flash_version: 4 or 7");
   g_flash_version.store(version);
   return WM_OK;
 }
@@ -303,7 +303,7 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   if (int rc = make_map_2d(&tv, v, (uint64_t)v_rows, (uint64_t)v_width, (uint64_t)ldv, 128, "wm_attn_flash(v)")) return rc;
   trel = tq;
   if (rel_table != nullptr) {
-    if ((hd != 64 && hd != 80) || Tq != 4096 || Tk != 4096)
+    if ((hd != 64 && hd != 80) || Tq != 4096 || Tk > 4096)
       return fail(WM_ERR_SHAPE, "wm_attn_flash: rel-pos needs head dim 64 or 80 and 64x64 tokens");
     if (int rc = make_map_2d(&trel, rel_table, 256, (uint64_t)hd, (uint64_t)hd, 16, "wm_attn_flash(rel)")) return rc;
   }
@@ -312,11 +312,16 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldo = (int)ldo;
   p.use_relpos = rel_table != nullptr;
+  // head dim 64 (encoder global blocks of ViT-B / ViT-L, head-padded decoder attention): v7 (ring of three score buffers);
+  // head dims 80 / 128 (ViT-H, HFC cross-attention): v4
+  if (hd == 64 && g_flash_version.load() == 7)
+    return check_launch(wm::flash7_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v7)");
   return check_launch(wm::flash4_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v4)");
 }
 
 int wm_debug_flash_trace(uint64_t* host_out_3x64x4) {
-  const int rc = wm::flash4_read_trace(reinterpret_cast<unsigned long long*>(host_out_3x64x4));
+  const int rc = g_flash_version.load() == 7 ? wm::flash7_read_trace(reinterpret_cast<unsigned long long*>(host_out_3x64x4))
+                                             : wm::flash4_read_trace(reinterpret_cast<unsigned long long*>(host_out_3x64x4));
   if (rc != WM_OK)
     return fail(WM_ERR_ARCH, "wm_debug_flash_trace: only available in the diagnostics build (-DWM_F3_TRACE)");
   return WM_OK;

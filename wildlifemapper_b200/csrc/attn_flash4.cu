@@ -598,7 +598,9 @@ int flash4_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
                     const FlashParams& p, int hd, cudaStream_t st) {
   if (p.Tq < 1 || p.Tk < 1) return WM_ERR_SHAPE;
   if (p.use_relpos) {
-    if (p.Tq != 4096 || p.Tk != 4096) return WM_ERR_SHAPE;
+    // queries: the whole 64x64 grid; keys: its first Tk / 64 rows (the encoder always passes all 4096; fewer are accepted for
+    // measurements: time vs key count separates the per-step cost from the per-CTA prologue)
+    if (p.Tq != 4096 || p.Tk > 4096 || p.Tk % 128 != 0) return WM_ERR_SHAPE;
     if (hd == 64) return launch_flash4<64, true>(tq, tk, tv, trel, p, st);
     if (hd == 80) return launch_flash4<80, true>(tq, tk, tv, trel, p, st);
     return WM_ERR_SHAPE;

@@ -60,7 +60,10 @@ struct FlashParams {
 };
 int flash4_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
                     const FlashParams& p, int hd, cudaStream_t st);
+int flash7_dispatch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& trel,
+                    const FlashParams& p, int hd, cudaStream_t st);  // head dim 64 (attn_flash7.cu)
 int flash4_read_trace(unsigned long long* host_out);
+int flash7_read_trace(unsigned long long* host_out);
 int window2_read_trace(unsigned long long* host_out);  // diagnostics build (-DWM_F3_TRACE) only
 
 struct WindowParams {

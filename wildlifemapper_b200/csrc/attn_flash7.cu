@@ -45,8 +45,27 @@ __device__ __forceinline__ float f7_ex2_poly(float x) {
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
+// the same for a packed pair (FADD2 / FFMA2: 12 instructions per pair instead of 18)
+__device__ __forceinline__ void f7_ex2_poly2(uint64_t yp, float& e0, float& e1) {
+  float x0, x1;
+  unpk2(yp, x0, x1);
+  x0 = fminf(fmaxf(x0, -120.0f), 126.0f);
+  x1 = fminf(fmaxf(x1, -120.0f), 126.0f);
+  const uint64_t x = pk2(x0, x1);
+  const uint64_t t = add2(x, pk2(12582912.0f, 12582912.0f));
+  const uint64_t rr = add2(t, pk2(-12582912.0f, -12582912.0f));
+  const uint64_t f = fma2(rr, pk2(-1.0f, -1.0f), x);  // x - round(x), exact
+  uint64_t pp = fma2(f, pk2(0.0555041f, 0.0555041f), pk2(0.2402265f, 0.2402265f));
+  pp = fma2(pp, f, pk2(0.6931472f, 0.6931472f));
+  pp = fma2(pp, f, pk2(1.0f, 1.0f));
+  float p0, p1, t0, t1;
+  unpk2(pp, p0, p1);
+  unpk2(t, t0, t1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
 #ifndef WM_F7_POLY
-#define WM_F7_POLY 6
+#define WM_F7_POLY 0
 #endif
 
 // one stage of the lane-dependent down-shift of x[0 .. 64 + SH - 1): lanes with bit SH set take x[i + SH]
@@ -57,11 +76,10 @@ __device__ __forceinline__ void f7_barrel_stage(uint32_t (&x)[96], int lane) {
   for (int i = 0; i < 64 + SH - 1; ++i) x[i] = on ? x[i + SH] : x[i];  // ascending i: x[i + SH] is still the old value
 }
 
-#ifdef WM_F7_PARKED  // A/B: producer / issuer warps wait with a suspend-time hint instead of re-polling
-#define F7_ROLE_WAIT mbar_wait_parked
-#else
+// every lane of the waiting warp polls: measured FASTER than one polling lane + __syncwarp (707 vs 800 ns per step), and a
+// suspend-time hint ("parked" waits) is slower still (1300 ns): the wake-up latency sits on the critical path
+#define f7_wait mbar_wait
 #define F7_ROLE_WAIT mbar_wait
-#endif
 
 constexpr int F7_THREADS = 384;
 constexpr int F7_NBUF = 3;  // score buffers per query tile
@@ -300,7 +318,7 @@ flash7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const uint32_t o_addr = lane_addr + Cfg::COL_O + t * HD;
     const float c1 = p.scale * F7_LOG2E;
     float tw[RELPOS ? 64 : 1];
-    const float* th = reinterpret_cast<const float*>(smem + Cfg::OFF_TH) + t * 128 + r;  // + 256 * key row
+    const uint32_t th_s = smem_u32(smem + Cfg::OFF_TH) + (uint32_t)(t * 128 + r) * 4u;  // + 1024 * key row
 
     if (RELPOS) {
       const int qj = (m0 + t * 128 + r) & 63;
@@ -362,36 +380,62 @@ flash7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     float m_ref = -INFINITY, l_run = 0.0f;
     int buf = 0;
     uint32_t ph = 0;
+    uint32_t sj = s_addr;  // this step's score buffer; P = bf16 pairs over its first 32 columns
     const uint64_t c1p = pk2(c1, c1);
+    // Software pipeline over the steps (the ring of three buffers gives the slack for it): the publication of P(j)
+    // (tcgen05.wait::st, fence, warp barrier, arrive) is DEFERRED until the score loads of step j+1 are in flight, and chunk 1
+    // of a step is loaded while its chunk 0 is processed.  Measured per 64-key step with rel-pos (profiles/flash_time2.py,
+    // batch 32): neither 853 ns, deferred publication 780, + chunk 0 of step j+1 requested during chunk 1 of step j
+    // (-DWM_F7_PREFETCH) 787; FMA-pipe exp2 for 3 of 16 pairs (-DWM_F7_POLY=6) costs more issue slots than it saves MUFU
+    // time here: 745 ns without it (v4: 800).
+    uint32_t v[2][32];
+    f7_wait(&s_full[t * NB], 0);
+    tc_fence_after();
+    tmem_ld32(sj, v[0]);
     for (int j = 0; j < ns; ++j) {  // one step = 64 keys = key row j of the 64x64 grid
-      const uint32_t sj = s_addr + buf * 64;  // this step's score buffer; P = bf16 pairs over its first 32 columns
       float bh = 0.0f;
-      if (RELPOS) bh = th[j * 256];
+      if (RELPOS) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bh) : "r"(th_s + (uint32_t)j * 1024u));
       if (q4 == 0 && lane == 0) F7_TRACE(t, j, 0);
-      mbar_wait(&s_full[t * NB + buf], ph);
-      tc_fence_after();
-      if (q4 == 0 && lane == 0) F7_TRACE(t, j, 1);
-      // One pass over the 64 scores of this row in two 32-column chunks.  Each chunk is first evaluated OPTIMISTICALLY
-      // against the current reference maximum; only if the chunk's row sum says that some probability of some row of the
-      // warp may exceed 2^TAU is the reference raised (O, l and the chunk of P already written are rescaled) and the
-      // chunk recomputed from the registers that still hold it.
-      uint32_t v[2][32];
-      tmem_ld32(sj, v[0]);
-      tmem_ld32(sj + 32, v[1]);
-      tmem_ld_wait();
-      if (!RELPOS && (j + 1) * 64 > p.Tk) {  // ragged last step: keys >= Tk get a score of -inf (exp2 -> 0)
-        const int nvalid = p.Tk - j * 64;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i >= nvalid) v[0][i] = 0xff800000u;
-          if (32 + i >= nvalid) v[1][i] = 0xff800000u;
-        }
+#ifndef WM_F7_PREFETCH
+      if (j > 0) {
+        f7_wait(&s_full[t * NB + buf], ph);
+        tc_fence_after();
+        tmem_ld32(sj, v[0]);
       }
+#endif
+      tmem_ld_wait();                // chunk 0 (requested during the previous step) has landed
+      tmem_ld32(sj + 32, v[1]);      // chunk 1: in flight while chunk 0 is processed
+#ifndef WM_F7_NO_DEFER
+      if (j > 0) {                   // publish P(j-1): its stores were issued at the end of the previous step
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t * NB + (buf == 0 ? NB - 1 : buf - 1)]);
+      }
+#endif
+      if (q4 == 0 && lane == 0) F7_TRACE(t, j, 1);
+      const int nvalid = (!RELPOS && (j + 1) * 64 > p.Tk) ? p.Tk - j * 64 : 64;  // ragged last step: keys >= Tk get -inf (exp2 -> 0)
       float l_step = 0.0f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t(&cur)[32] = v[c];
-        float d = RELPOS ? bh - m_ref : -m_ref;  // +inf while m_ref = -inf: the first chunk always takes the exact path
+        if (c == 1) {
+          tmem_ld_wait();  // chunk 1 has landed (requested before chunk 0 was processed)
+#ifdef WM_F7_PREFETCH
+          if (j + 1 < ns) {  // request chunk 0 of the next step into the registers chunk 0 just vacated
+            const int nb = buf + 1 == NB ? 0 : buf + 1;
+            f7_wait(&s_full[t * NB + nb], buf + 1 == NB ? ph ^ 1u : ph);
+            tc_fence_after();
+            tmem_ld32(buf + 1 == NB ? s_addr : sj + 64, v[0]);
+          }
+#endif
+        }
+        if (!RELPOS && nvalid < 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= nvalid) cur[i] = 0xff800000u;
+        }
+        float d = bh - m_ref;  // +inf while m_ref = -inf: the first chunk always takes the exact path
         uint64_t cs2[2] = {0ull, 0ull};  // 2 x 2 partial row sums (packed fp32x2)
         uint32_t pk[16];
         {
@@ -402,10 +446,15 @@ flash7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             uint64_t yp;
             if (RELPOS) yp = add2(fma2(vp, c1p, pk2(tw[RELPOS ? c * 32 + 2 * i : 0], tw[RELPOS ? c * 32 + 2 * i + 1 : 0])), dp);
             else yp = fma2(vp, c1p, dp);
-            float a0, a1;
-            unpk2(yp, a0, a1);
-            const bool poly = WM_F7_POLY > 0 && (i % (WM_F7_POLY > 0 ? WM_F7_POLY : 1)) == 0;
-            const float e0 = poly ? f7_ex2_poly(a0) : ex2_approx(a0), e1 = poly ? f7_ex2_poly(a1) : ex2_approx(a1);
+            float e0, e1;
+            if (WM_F7_POLY > 0 && (i % (WM_F7_POLY > 0 ? WM_F7_POLY : 1)) == 0) {
+              f7_ex2_poly2(yp, e0, e1);
+            } else {
+              float a0, a1;
+              unpk2(yp, a0, a1);
+              e0 = ex2_approx(a0);
+              e1 = ex2_approx(a1);
+            }
             cs2[i & 1] = add2(cs2[i & 1], pk2(e0, e1));
             pk[i] = pack_bf16(e0, e1);
           }
@@ -423,20 +472,20 @@ flash7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             const float y = RELPOS ? fmaf(__uint_as_float(cur[i]), c1, tw[RELPOS ? c * 32 + i : 0]) : __uint_as_float(cur[i]) * c1;
             ymax = fmaxf(ymax, y);
           }
-          const float m_chunk = RELPOS ? ymax + bh : ymax;
+          const float m_chunk = ymax + bh;
           const float m_new = need ? fmaxf(m_chunk, m_ref) : m_ref;
           const float alpha = ex2_approx(m_ref - m_new);  // 1 for lanes that did not need it, 0 on the very first chunk
           if (j > 0) {
             // O must be stable: P_t(j-1) V is the last MMA that touches O_t before p_full(j).  It was issued ahead of
-            // S_t(j+2): wait for that score tile (a peek -- the barrier is waited on again at step j + 2); the last two steps
+            // S_t(j+2): wait for that score tile (a peek -- the barrier is waited on again later); the last two steps
             // have no such tile and use the single-use barriers.
             if (j + 2 < ns) {
               int b2 = buf + 2;
               uint32_t ph2 = ph;
               if (b2 >= NB) { b2 -= NB; ph2 ^= 1u; }
-              mbar_wait(&s_full[t * NB + b2], ph2);
+              f7_wait(&s_full[t * NB + b2], ph2);
             } else {
-              mbar_wait(&pv_tail[t * 2 + (j + 2 - ns)], 0);
+              f7_wait(&pv_tail[t * 2 + (j + 2 - ns)], 0);
             }
             tc_fence_after();
 #pragma unroll
@@ -464,7 +513,7 @@ flash7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             l_step *= alpha;
           }
           m_ref = m_new;
-          d = RELPOS ? bh - m_ref : -m_ref;
+          d = bh - m_ref;
           cs2[0] = 0ull;
           cs2[1] = 0ull;
           const uint64_t dp = pk2(d, d);
@@ -485,18 +534,28 @@ flash7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           csum = (s0 + s1) + (s2 + s3);
         }
         l_step += csum;
-        // P chunk c (16 columns of bf16 pairs) overwrites score columns [16c, 16c+16) of chunk 0, which is in registers
+        // P chunk c (16 columns of bf16 pairs) overwrites score columns [16c, 16c+16): chunk 0's, long in registers
         tmem_st16(sj + c * 16, pk);
       }
       l_run += l_step;
       if (q4 == 0 && lane == 0) F7_TRACE(t, j, 2);
+#ifdef WM_F7_NO_DEFER
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t * NB + buf]);
-      if (q4 == 0 && lane == 0) F7_TRACE(t, j, 3);
-      if (++buf == NB) { buf = 0; ph ^= 1u; }
+#endif
+      sj += 64;
+      if (++buf == NB) { buf = 0; ph ^= 1u; sj = s_addr; }
     }
+#ifndef WM_F7_NO_DEFER
+    {  // publish the last P
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t * NB + (buf == 0 ? NB - 1 : buf - 1)]);
+    }
+#endif
     // ---- epilogue: O / l
     mbar_wait(&o_full[t], 0);
     tc_fence_after();

@@ -243,7 +243,18 @@ int add_cast_launch(const float* a, const float* b, int b_mod, __nv_bfloat16* ou
 // in smem as fp32 and read by broadcast (all threads of a warp read the same key), online softmax in the exp2
 // domain over chunks of 8 keys.  SPLIT = 4 partitions every key tile across 4 thread groups (for few queries,
 // e.g. 51 tokens -> image) and merges the partial (m, l, acc) through smem.
-template <int HD, int SPLIT>
+//
+// KSPLIT > 1 (few queries against many keys: 51 tokens -> 4096 image positions is a 256-CTA launch otherwise, 1.7 CTAs per
+// SM each walking 32 key tiles): a thread-block CLUSTER of KSPLIT CTAs shares the queries of one block, CTA `rank` takes
+// the key tiles rank, rank + KSPLIT, ...; the partial softmax states are merged by rank 0 through distributed shared
+// memory (flash-decoding inside a cluster: no second kernel, no global scratch).
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+
+template <int HD, int SPLIT, int KSPLIT>
 __global__ void __launch_bounds__(256) attn_small_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
                                                          const __nv_bfloat16* __restrict__ k, int ldk,
                                                          const __nv_bfloat16* __restrict__ v, int ldv,
@@ -255,7 +266,8 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const __nv_bfloat16* __
   __shared__ __align__(16) float sV[128][HD];
   const int h = blockIdx.y, b = blockIdx.z;
   const int grp = threadIdx.x / QB, ql = threadIdx.x % QB;
-  const int qi = blockIdx.x * QB + ql;
+  const int krank = KSPLIT > 1 ? (int)(blockIdx.x % KSPLIT) : 0;  // (cluster dims (KSPLIT,1,1): rank == blockIdx.x % KSPLIT)
+  const int qi = (int)(blockIdx.x / KSPLIT) * QB + ql;
   const bool q_ok = qi < Tq;
   float qr[HD], acc[HD];
 #pragma unroll
@@ -275,7 +287,7 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const __nv_bfloat16* __
     }
   }
   float m_run = -INFINITY, l_run = 0.f;
-  for (int k0 = 0; k0 < Tk; k0 += 128) {
+  for (int k0 = krank * 128; k0 < Tk; k0 += 128 * KSPLIT) {
     __syncthreads();
     // stage 128 keys x HD of K and V (16-byte global loads, zero fill past Tk)
     for (int i = threadIdx.x; i < 128 * (HD / 8); i += 256) {
@@ -360,6 +372,37 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const __nv_bfloat16* __
       }
     }
     __syncthreads();
+    if (KSPLIT > 1) {
+      // cross-CTA merge: every CTA publishes (m_all, merged l, merged acc) of its key subset, rank 0 combines them
+      float* smx = sl + (SPLIT + 1) * QB;  // [QB] m_all of this CTA
+      if (grp == 0) smx[ql] = m_all;
+      cluster_sync();
+      if (krank == 0 && grp == 0) {
+        float mg = -INFINITY;
+#pragma unroll
+        for (int rk = 0; rk < KSPLIT; ++rk) mg = fmaxf(mg, ld_dsmem_f32(mapa_shared(smem_u32(smx + ql), rk)));
+        float lg = 0.f, og[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) og[d] = 0.f;
+#pragma unroll 1
+        for (int rk = 0; rk < KSPLIT; ++rk) {
+          const float mr = ld_dsmem_f32(mapa_shared(smem_u32(smx + ql), rk));
+          const float wr = (mr == -INFINITY) ? 0.f : ex2_approx(mr - mg);
+          lg = fmaf(ld_dsmem_f32(mapa_shared(smem_u32(sl + SPLIT * QB + ql), rk)), wr, lg);
+          const uint32_t ar = mapa_shared(smem_u32(sa + (size_t)ql * HD), rk);
+#pragma unroll
+          for (int d = 0; d < HD; ++d) og[d] = fmaf(ld_dsmem_f32(ar + 4 * d), wr, og[d]);
+        }
+        if (q_ok) {
+          const float inv = 1.0f / lg;
+          __nv_bfloat16* op = out + (size_t)(b * Tq + qi) * ldo + h * HD;
+#pragma unroll
+          for (int d = 0; d < HD; d += 2) *reinterpret_cast<uint32_t*>(op + d) = pack_bf16(og[d] * inv, og[d + 1] * inv);
+        }
+      }
+      cluster_sync();  // the peers' shared memory must stay alive until rank 0 has read it
+      return;
+    }
     if (grp == 0 && q_ok) {
       const float inv = 1.0f / sl[SPLIT * QB + ql];
       __nv_bfloat16* op = out + (size_t)(b * Tq + qi) * ldo + h * HD;
@@ -378,14 +421,256 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const __nv_bfloat16* __
   }
 }
 
+// ------------------------------------------------------------------ decoder attention on warp-level tensor-core MMAs
+// The three decoder shapes (tokens self-attention 51 x 51 x 32, tokens -> image 51 x 4096 x 16, image -> tokens
+// 4096 x 51 x 16; transformer.py:218-240) are 3.5 GFLOP per tile batch: nothing for the tensor cores, but the
+// thread-per-query kernel above needs one shared-memory broadcast load per 4 FMAs and ran them at 32 / 253 / 143 us
+// (1.1 ms of the 42 ms step).  Head dims of 16 / 32 are one or two K = 16 steps: the warp-level mma.sync m16n8k16 form fits
+// exactly (a tcgen05 tile would be 128 x N x 16 with 51 live rows and a TMEM round trip per 64 keys; this op is
+// latency-bound, not throughput-bound).  One warp = 16 queries, FlashAttention-2 register layout: the S accumulators of two
+// n8 tiles are the A fragment of the P V product, K fragments are plain 32-bit shared loads, V fragments come from
+// ldmatrix.trans.  Many keys, few queries: the keys are split over a CLUSTER of KSPLIT CTAs and merged by rank 0 through
+// distributed shared memory (no second kernel, no global scratch).
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_addr));
+}
+
+template <int HD, int KSPLIT>
+__global__ void __launch_bounds__(128) attn_mma_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
+                                                       const __nv_bfloat16* __restrict__ k, int ldk,
+                                                       const __nv_bfloat16* __restrict__ v, int ldv,
+                                                       __nv_bfloat16* __restrict__ out, int ldo, int Tq, int Tk,
+                                                       float scale_log2e) {
+  constexpr int KT = 64;             // keys per staged tile
+  constexpr int ROWB = HD * 2 + 16;  // smem row pitch in bytes (+16: ldmatrix / fragment loads without bank conflicts)
+  __shared__ __align__(16) uint8_t sK[KT * ROWB];
+  __shared__ __align__(16) uint8_t sV[KT * ROWB];
+  __shared__ float sM[64], sL[64], sO[64][HD];  // published partial state (cluster merge)
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int krank = KSPLIT > 1 ? (int)(blockIdx.x % KSPLIT) : 0;
+  const int q0 = (int)(blockIdx.x / KSPLIT) * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  // ---- Q fragments (A operand): rows g and g + 8 of this warp's 16 queries, straight from global (zero beyond Tq)
+  uint32_t qa[HD / 16][4];
+  {
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+    const __nv_bfloat16* p0 = q + (size_t)(b * Tq + r0) * ldq + h * HD;
+    const __nv_bfloat16* p1 = q + (size_t)(b * Tq + r1) * ldq + h * HD;
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      qa[ks][0] = r0 < Tq ? __ldg(reinterpret_cast<const uint32_t*>(p0 + ks * 16 + 2 * t4)) : 0u;
+      qa[ks][1] = r1 < Tq ? __ldg(reinterpret_cast<const uint32_t*>(p1 + ks * 16 + 2 * t4)) : 0u;
+      qa[ks][2] = r0 < Tq ? __ldg(reinterpret_cast<const uint32_t*>(p0 + ks * 16 + 8 + 2 * t4)) : 0u;
+      qa[ks][3] = r1 < Tq ? __ldg(reinterpret_cast<const uint32_t*>(p1 + ks * 16 + 8 + 2 * t4)) : 0u;
+    }
+  }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float o[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+
+  for (int k0 = krank * KT; k0 < Tk; k0 += KT * KSPLIT) {
+    __syncthreads();
+    // stage 64 keys x HD of K and V (16-byte loads, zero fill past Tk)
+    for (int i = threadIdx.x; i < KT * (HD / 8); i += 128) {
+      const int kk = i / (HD / 8), d8 = i % (HD / 8);
+      uint4 uk = make_uint4(0, 0, 0, 0), uv = make_uint4(0, 0, 0, 0);
+      if (k0 + kk < Tk) {
+        uk = __ldg(reinterpret_cast<const uint4*>(k + (size_t)(b * Tk + k0 + kk) * ldk + h * HD) + d8);
+        uv = __ldg(reinterpret_cast<const uint4*>(v + (size_t)(b * Tk + k0 + kk) * ldv + h * HD) + d8);
+      }
+      *reinterpret_cast<uint4*>(sK + kk * ROWB + d8 * 16) = uk;
+      *reinterpret_cast<uint4*>(sV + kk * ROWB + d8 * 16) = uv;
+    }
+    __syncthreads();
+    // ---- S = Q K^T for the 64 keys of the tile: 8 n8 tiles, accumulators s[j] = (row g: keys 8j + 2 t4, +1; row g + 8: same)
+    float sc[KT / 8][4];
+#pragma unroll
+    for (int j = 0; j < KT / 8; ++j) {
+      sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        const uint8_t* kr = sK + (8 * j + g) * ROWB + ks * 32 + 4 * t4;  // B[k = dim][n = key] = K[key][dim]
+        mma_bf16_16816(sc[j], qa[ks], *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 16));
+      }
+    }
+    // ---- online softmax (exp2 domain); rows g (c0, c1) and g + 8 (c2, c3); a row lives in the 4 lanes of a quad
+    const int nvalid = Tk - k0;  // keys >= nvalid of this tile are padding
+    float mx[2] = {m_run[0], m_run[1]};
+#pragma unroll
+    for (int j = 0; j < KT / 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = 8 * j + 2 * t4 + (e & 1);
+        sc[j][e] = key < nvalid ? sc[j][e] * scale_log2e : -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], sc[j][e]);
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+    }
+    const float al[2] = {ex2_approx(m_run[0] - mx[0]), ex2_approx(m_run[1] - mx[1])};  // 0 on the first tile (every tile has a valid key)
+    m_run[0] = mx[0];
+    m_run[1] = mx[1];
+    l_run[0] *= al[0];
+    l_run[1] *= al[1];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      o[i][0] *= al[0]; o[i][1] *= al[0];
+      o[i][2] *= al[1]; o[i][3] *= al[1];
+    }
+    // ---- P V: 16 keys per k-step; the accumulators of n8 tiles 2 kk and 2 kk + 1 ARE the A fragment of k-step kk
+#pragma unroll
+    for (int kk = 0; kk < KT / 16; ++kk) {
+      uint32_t pa[4];
+      float e[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        e[u] = ex2_approx(sc[2 * kk + (u >> 2)][u & 3] - mx[(u >> 1) & 1]);  // masked keys: exp2(-inf) = 0
+        l_run[(u >> 1) & 1] += e[u];
+      }
+      pa[0] = pack_bf16(e[0], e[1]);  // row g,     keys 16 kk + 2 t4, +1
+      pa[1] = pack_bf16(e[2], e[3]);  // row g + 8
+      pa[2] = pack_bf16(e[4], e[5]);  // row g,     keys 16 kk + 8 + 2 t4, +1
+      pa[3] = pack_bf16(e[6], e[7]);  // row g + 8
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        uint32_t b0, b1;  // B[k = key][n = dim] = V[key][dim]: two transposed 8 x 8 tiles (keys 16 kk .. +7, +8 .. +15)
+        ldmatrix_x2_trans(b0, b1, smem_u32(sV + (16 * kk + (lane & 15)) * ROWB + i * 16));
+        mma_bf16_16816(o[i], pa, b0, b1);
+      }
+    }
+  }
+  // row sums: a row's l is spread over the 4 lanes of its quad
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 1);
+    l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 2);
+  }
+  const int row0 = warp * 16 + g;  // local query rows row0, row0 + 8
+  if (KSPLIT > 1) {
+    if (t4 == 0) {
+      sM[row0] = m_run[0]; sM[row0 + 8] = m_run[1];
+      sL[row0] = l_run[0]; sL[row0 + 8] = l_run[1];
+    }
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      sO[row0][8 * i + 2 * t4] = o[i][0]; sO[row0][8 * i + 2 * t4 + 1] = o[i][1];
+      sO[row0 + 8][8 * i + 2 * t4] = o[i][2]; sO[row0 + 8][8 * i + 2 * t4 + 1] = o[i][3];
+    }
+    cluster_sync();
+    if (krank == 0 && threadIdx.x < 64) {  // thread = one query row
+      const int rr = threadIdx.x;
+      float mg = -INFINITY;
+#pragma unroll
+      for (int rk = 0; rk < KSPLIT; ++rk) mg = fmaxf(mg, ld_dsmem_f32(mapa_shared(smem_u32(&sM[rr]), rk)));
+      float lg = 0.f, og[HD];
+#pragma unroll
+      for (int d = 0; d < HD; ++d) og[d] = 0.f;
+#pragma unroll 1
+      for (int rk = 0; rk < KSPLIT; ++rk) {
+        const float mr = ld_dsmem_f32(mapa_shared(smem_u32(&sM[rr]), rk));
+        const float wr = (mr == -INFINITY) ? 0.f : ex2_approx(mr - mg);
+        lg = fmaf(ld_dsmem_f32(mapa_shared(smem_u32(&sL[rr]), rk)), wr, lg);
+        const uint32_t ar = mapa_shared(smem_u32(&sO[rr][0]), rk);
+#pragma unroll
+        for (int d = 0; d < HD; ++d) og[d] = fmaf(ld_dsmem_f32(ar + 4 * d), wr, og[d]);
+      }
+      if (q0 + rr < Tq) {
+        const float inv = 1.0f / lg;
+        __nv_bfloat16* op = out + (size_t)(b * Tq + q0 + rr) * ldo + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; d += 2) *reinterpret_cast<uint32_t*>(op + d) = pack_bf16(og[d] * inv, og[d + 1] * inv);
+      }
+    }
+    cluster_sync();  // the peers' shared memory must stay alive until rank 0 has read it
+  } else {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int qi = q0 + row0 + 8 * hh;
+      if (qi < Tq) {
+        const float inv = 1.0f / l_run[hh];
+        __nv_bfloat16* op = out + (size_t)(b * Tq + qi) * ldo + h * HD;
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i)
+          *reinterpret_cast<uint32_t*>(op + 8 * i + 2 * t4) = pack_bf16(o[i][2 * hh] * inv, o[i][2 * hh + 1] * inv);
+      }
+    }
+  }
+}
+
+template <int HD, int KS>
+static int attn_mma_launch(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
+                           __nv_bfloat16* out, int ldo, int B, int H, int Tq, int Tk, float sl2, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(((Tq + 63) / 64) * KS, H, B);
+  cfg.blockDim = dim3(128, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = KS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = KS > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, attn_mma_kernel<HD, KS>, q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, sl2) == cudaSuccess
+             ? WM_OK : WM_ERR_CUDA;
+}
+
 int attn_small_launch(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
                       __nv_bfloat16* out, int ldo, int B, int H, int Tq, int Tk, int hd, float scale, cudaStream_t st) {
   if (B * H * Tq == 0) return WM_OK;
   if ((ldq | ldk | ldv | ldo) % 8 != 0) return WM_ERR_SHAPE;
   const float sl2 = scale * 1.4426950408889634f;
+  if ((ldq | ldk | ldv | ldo) % 8 == 0 && ((Tq + 63) / 64) * 8 <= 65535) {
+    // tensor-core path (every decoder shape); few queries against many keys: keys split over a small cluster
+    // Cluster size of the key split, measured at 51 x 4096 x 16, batch 32 (profiles/attn_small_scan.py): 1 CTA 60.6 us,
+    // 2: 53.8, 4: 60.2, 8: 90.3 -- cluster launches carry a fixed cost that grows with the cluster size (~67 us at 8), the
+    // per-tile cost is the same.  (Thread-per-query CUDA-core kernel: 253 us.)
+#ifndef WM_ATTN_KS
+#define WM_ATTN_KS 2
+#endif
+    const bool ks8 = Tq <= 256 && Tk >= 1024;
+    if (hd == 16) return ks8 ? attn_mma_launch<16, WM_ATTN_KS>(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Tq, Tk, sl2, st)
+                             : attn_mma_launch<16, 1>(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Tq, Tk, sl2, st);
+    if (hd == 32) return ks8 ? attn_mma_launch<32, WM_ATTN_KS>(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Tq, Tk, sl2, st)
+                             : attn_mma_launch<32, 1>(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Tq, Tk, sl2, st);
+    return WM_ERR_SHAPE;
+  }
   const bool split = Tq <= 1024;
+  // few queries, many keys (tokens -> image): split the keys over a cluster of 8 CTAs
+  const bool ksplit = split && Tk >= 2048;
+  if (ksplit) {
+    constexpr int KS = 8;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(((Tq + 63) / 64) * KS, H, B);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = KS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    if (hd == 16) e = cudaLaunchKernelEx(&cfg, attn_small_kernel<16, 4, KS>, q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, sl2);
+    else if (hd == 32) e = cudaLaunchKernelEx(&cfg, attn_small_kernel<32, 4, KS>, q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, sl2);
+    else return WM_ERR_SHAPE;
+    return e == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+  }
   dim3 grid((Tq + (split ? 63 : 255)) / (split ? 64 : 256), H, B);
-#define WM_AS(HD_, SP_) attn_small_kernel<HD_, SP_><<<grid, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, sl2)
+#define WM_AS(HD_, SP_) attn_small_kernel<HD_, SP_, 1><<<grid, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, sl2)
   if (hd == 16) { if (split) WM_AS(16, 4); else WM_AS(16, 1); }
   else if (hd == 32) { if (split) WM_AS(32, 4); else WM_AS(32, 1); }
   else return WM_ERR_SHAPE;

@@ -61,6 +61,9 @@ int wm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const f
                  int64_t ldr, int res_mod, void* out_bf16, int64_t ldc_bf16, float* out_f32, int64_t ldc_f32, int M,
                  int N, int K, int act, int bn_hint, void* stream);
 
+/* SM count of the current device (> 0), or a negative WM_ERR_* code */
+int wm_num_sms(void);
+
 /* 3x3, pad 1, no-bias convolution on NHWC bf16 [B,64,64,C] as an implicit GEMM; W is [N, 9*C] bf16 with
  * k = (dy*3+dx)*C + c.  Replaces neck[2], image_encoder.py:113-119.  Output rows = pixels, [B*4096, N]. */
 int wm_conv3x3_nhwc_bf16(const void* X, const void* W, void* out_bf16, float* out_f32, int B, int C, int N,
@@ -151,6 +154,17 @@ int wm_nms_batched(const float* packed, const int32_t* counts, int B, int Q, flo
  * (utils/misc.py:46-67); bit-exact (IEEE division, same operation order).  mean/std: host pointers to 3 floats. */
 int wm_tiles_from_u8(const uint8_t* img, int H, int W, int64_t row_stride, const int32_t* origins, int T, int content_h,
                      int content_w, const float* mean3, const float* std3, float* out, void* stream);
+
+/* PIL-exact bilinear (antialiased) resize of T uint8 RGB tiles (tile_h x tile_w windows of ONE uint8 HWC image at origins
+ * int32 [T,2] = (y0, x0), fully inside the image) to out_h x out_w: out uint8 [T,out_h,out_w,3]; tmp uint8 [T,tile_h,out_w,3]
+ * is the intermediate of the horizontal pass.  Replaces RandomResize([768], max_size=768) of the reference's transforms
+ * (dataloader_coco.py:275-292 -> utils/augmentation.py:77-107 -> torchvision F.resize -> PIL Image.resize(BILINEAR)).
+ * xbounds / ybounds int32 [out,2] = (first input index, tap count), xk / yk int32 [out, ksize] = PIL's 22-bit fixed-point
+ * coefficients (device pointers; the host computes them exactly as Pillow's precompute_coeffs + normalize_coeffs_8bpc do).
+ * Bit-exact with Pillow: 8-bit intermediate, (2^21 + sum) >> 22, clipped. */
+int wm_resize_tiles_u8(const uint8_t* img, int img_h, int img_w, int64_t row_stride, const int32_t* origins, int T, int tile_h,
+                       int tile_w, uint8_t* tmp, uint8_t* out, int out_h, int out_w, const int32_t* xbounds, const int32_t* xk,
+                       int xksize, const int32_t* ybounds, const int32_t* yk, int yksize, void* stream);
 
 /* Image-level candidate list from the packed per-tile PostProcess rows (packed fp32 [T,Q,6], counts int32 [T], Q <= 1024):
  * rows with score > score_thr (visualize_prediction.py:150) in tile-major, query order; boxes moved by the tile origin

@@ -13,7 +13,15 @@ numpy restatement of the steps either side of the tile-detection path (SURVEY.md
                     extension).
   to_xywh           ``convert_to_xywh`` (inference.py:235-237): (xmin, ymin, xmax - xmin, ymax - ymin).
 
-``tests/test_oracle_frontend.py`` pins ``tiles_from_u8`` against a golden minted by running the reference's own
+  resize_u8         PIL ``Image.resize(size, BILINEAR)`` on an 8-bit RGB image -- what ``RandomResize([768], max_size=768)``
+                    (dataloader_coco.py:275-292 -> utils/augmentation.py:77-107 -> torchvision F.resize) does to a tile --
+                    restated from Pillow's src/libImaging/Resample.c (precompute_coeffs, normalize_coeffs_8bpc,
+                    ImagingResampleHorizontal_8bpc / Vertical_8bpc; Pillow is a third-party dependency of the reference,
+                    12.2.0 in this image): double-precision triangle-filter taps scaled by max(scale, 1), rounded to
+                    22-bit integers, horizontal pass into a uint8 intermediate, vertical pass, clip8.
+
+``tests/test_oracle_frontend.py`` pins ``resize_u8`` against PIL itself (and a golden minted through the reference's
+``resize`` transform), and pins ``tiles_from_u8`` against a golden minted by running the reference's own
 transform classes and ``nested_tensor_from_tensor_list`` (tests/golden/make_golden.py), and ``to_xywh`` against the torch
 expression of the reference.
 """
@@ -78,6 +86,14 @@ FRONTEND_CASES = (
 )
 
 
+# resize cases: tag, tile (H, W), RandomResize size / max_size  (the reference uses ([768], 768) on its tile files)
+RESIZE_CASES = (
+    ("rs1024", (1024, 1024), 768, 768),   # the loader's case: a 1024 x 1024 tile -> 768 x 768
+    ("rs_wide", (600, 900), 768, 768),    # aspect ratio: max_size caps the long side -> (512, 768)
+    ("rs_up", (300, 240), 768, 768),      # upscaling (w < h: width -> 614?, decided by get_size_with_aspect_ratio)
+)
+
+
 def frontend_image(tag: str, hw) -> np.ndarray:
     import zlib
     return np.random.default_rng(zlib.crc32(tag.encode())).integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
@@ -97,3 +113,51 @@ def make_tile_detections(T: int, Q: int, seed: int = 7):
     counts[0] = 0
     counts[-1] = Q
     return packed, counts
+
+
+def pil_bilinear_coeffs(in_size: int, out_size: int):
+    """Resample.c precompute_coeffs (box = whole image, bilinear filter, support 1) + normalize_coeffs_8bpc.
+    -> bounds int32 [out, 2] (xmin, count), kk int32 [out, ksize]."""
+    scale = np.float64(in_size) / np.float64(out_size)
+    filterscale = max(scale, np.float64(1.0))
+    support = np.float64(1.0) * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    ss = np.float64(1.0) / filterscale
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    for xx in range(out_size):
+        center = np.float64(0.0) + (xx + np.float64(0.5)) * scale
+        xmin = max(int(np.trunc(center - support + 0.5)), 0)
+        xmax = min(int(np.trunc(center + support + 0.5)), in_size) - xmin
+        xs = np.arange(xmax, dtype=np.float64)
+        a = np.abs((xs + xmin - center + 0.5) * ss)
+        w = np.where(a < 1.0, 1.0 - a, 0.0)
+        ww = np.float64(0.0)
+        for v in w:  # sequential sum, as in the C loop
+            ww = ww + v
+        if ww != 0.0:
+            w = w / ww
+        bounds[xx] = (xmin, xmax)
+        kk[xx, :xmax] = np.trunc(np.where(w < 0, -0.5, 0.5) + w * np.float64(1 << 22)).astype(np.int64)
+    return bounds, kk
+
+
+def resize_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """uint8 [H,W,3] -> uint8 [out_h,out_w,3], Pillow's two-pass 8-bit resampling (horizontal first)."""
+    assert img.dtype == np.uint8 and img.ndim == 3
+    H, W, C = img.shape
+
+    def one_pass(src: np.ndarray, n_in: int, n_out: int) -> np.ndarray:  # resamples axis 1 of src [R, n_in, C]
+        if n_in == n_out:
+            return src
+        bounds, kk = pil_bilinear_coeffs(n_in, n_out)
+        out = np.empty((src.shape[0], n_out, C), np.uint8)
+        s64 = src.astype(np.int64)
+        for xx in range(n_out):
+            lo, cnt = bounds[xx]
+            acc = (1 << 21) + np.tensordot(s64[:, lo:lo + cnt, :], kk[xx, :cnt].astype(np.int64), axes=([1], [0]))
+            out[:, xx, :] = np.clip(acc >> 22, 0, 255).astype(np.uint8)
+        return out
+
+    tmp = one_pass(img, W, out_w)                                   # [H, out_w, C]
+    return one_pass(tmp.transpose(1, 0, 2), H, out_h).transpose(1, 0, 2)  # vertical pass on the transposed view

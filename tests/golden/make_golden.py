@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 REF = "/root/reference/wildlifemapper"
 
 from oracle import post as opost  # noqa: E402
-from oracle.frontend import FRONTEND_CASES, frontend_image  # noqa: E402
+from oracle.frontend import FRONTEND_CASES, RESIZE_CASES, frontend_image  # noqa: E402
 from oracle.weights import MODEL_CONFIGS, make_state_dict, make_tiles  # noqa: E402
 
 N_SAMPLES = 256
@@ -182,6 +182,14 @@ def golden_frontend() -> None:
         res[f"{tag}.sha256"] = np.array(hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest())
         res[f"{tag}.samples"] = out.reshape(-1)[sample_positions(out.size, tag)]
         res[f"{tag}.sum"] = np.array([np.abs(out.astype(np.float64)).sum()])
+    # RandomResize([768], max_size=768) (dataloader_coco.py:277,288 -> augmentation.py:77-107 -> torchvision F.resize -> PIL)
+    for tag, hw, size, max_size in RESIZE_CASES:
+        img = frontend_image(tag, hw)
+        out, _ = T.RandomResize([size], max_size=max_size)(Image.fromarray(img), None)
+        arr = np.asarray(out)
+        res[f"{tag}.shape"] = np.array(arr.shape[:2])
+        res[f"{tag}.sha256"] = np.array(hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest())
+        res[f"{tag}.samples"] = arr.reshape(-1)[sample_positions(arr.size, tag)]
     # convert_to_xywh lives in inference.py, which does not import here (pycocotools): run its source text
     src = open(os.path.join(REF, "inference.py")).read()
     m = re.search(r"^def convert_to_xywh\(boxes\):\n(?:[ \t]+.*\n)+", src, re.M)

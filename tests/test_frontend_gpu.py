@@ -108,3 +108,31 @@ def test_survey_detector_end_to_end_matches_tilewise_path():
     np.testing.assert_array_equal(res["src"].cpu().numpy(), ref["src"])
     np.testing.assert_array_equal(res["boxes"].cpu().numpy(), ref["boxes"])
     np.testing.assert_array_equal(res["keep"].cpu().numpy(), opost.batched_nms(ref["boxes"], ref["scores"], ref["labels"], 0.4))
+
+
+@pytest.mark.parametrize("case", of.RESIZE_CASES, ids=[c[0] for c in of.RESIZE_CASES])
+def test_resize_tiles_u8_golden_bit_exact(golden_dir, case):
+    """wm_resize_tiles_u8 vs the golden minted through the reference's RandomResize transform (PIL): sha256-exact."""
+    tag, hw, _size, _max = case
+    g = np.load(os.path.join(golden_dir, "golden_frontend.npz"))
+    oh, ow = (int(v) for v in g[f"{tag}.shape"])
+    img = torch.from_numpy(of.frontend_image(tag, hw)).to(DEV)
+    out = survey.resize_tiles_u8(img, torch.tensor([[0, 0]], dtype=torch.int32, device=DEV), hw, (oh, ow))[0].cpu().numpy()
+    assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == str(g[f"{tag}.sha256"])
+
+
+def test_resize_tiles_u8_survey_windows_bit_exact():
+    """Several 1024 x 1024 windows of one survey image -> 768 x 768 (the loader's case), against the oracle per tile, and
+    chained into tiles_from_u8: the reference's "768 x 768 content in a 1024 x 1024 canvas" tensor, bit-exact."""
+    H, W = 2200, 3000
+    img = of.frontend_image("survey_rs", (H, W))
+    org = [(0, 0), (1176, 1976), (500, 700)]
+    small = survey.resize_tiles_u8(torch.from_numpy(img).to(DEV), torch.tensor(org, dtype=torch.int32, device=DEV), (1024, 1024), (768, 768))
+    refs = [of.resize_u8(np.ascontiguousarray(img[y:y + 1024, x:x + 1024]), 768, 768) for y, x in org]
+    for t in range(len(org)):
+        np.testing.assert_array_equal(small[t].cpu().numpy(), refs[t])
+    T = len(org)
+    stacked = torch.tensor([[t * 768, 0] for t in range(T)], dtype=torch.int32, device=DEV)
+    tiles = survey.tiles_from_u8(small.view(T * 768, 768, 3), stacked, (768, 768)).cpu().numpy()
+    for t in range(T):
+        np.testing.assert_array_equal(tiles[t], of.tiles_from_u8(refs[t], [(0, 0)], (768, 768))[0])

@@ -59,3 +59,33 @@ def test_merge_detections_properties():
     m2 = of.merge_detections(packed2, counts2, [(0, 0), (0, 896)], 0.5)
     keep = op.batched_nms(m2["boxes"], m2["scores"], m2["labels"], 0.4)
     np.testing.assert_array_equal(keep, [0])
+
+
+@pytest.mark.parametrize("case", of.RESIZE_CASES, ids=[c[0] for c in of.RESIZE_CASES])
+def test_resize_u8_golden(golden_dir, case):
+    """oracle.frontend.resize_u8 vs the golden minted by the reference's RandomResize([768], max_size=768) transform (PIL)."""
+    tag, hw, _size, _max = case
+    g = np.load(os.path.join(golden_dir, "golden_frontend.npz"))
+    oh, ow = (int(v) for v in g[f"{tag}.shape"])
+    out = of.resize_u8(of.frontend_image(tag, hw), oh, ow)
+    np.testing.assert_array_equal(out.reshape(-1)[_sample_positions(out.size, tag)], g[f"{tag}.samples"])
+    assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == str(g[f"{tag}.sha256"])  # bit exact
+
+
+def test_resize_u8_matches_pil_directly():
+    PIL = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(3)
+    for (H, W, oh, ow) in [(64, 48, 48, 36), (100, 333, 77, 200), (50, 50, 120, 70), (31, 17, 5, 3), (40, 40, 40, 40)]:
+        a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        ref = np.asarray(PIL.fromarray(a).resize((ow, oh), PIL.BILINEAR))
+        np.testing.assert_array_equal(of.resize_u8(a, oh, ow), ref)
+
+
+def test_product_coefficients_equal_oracle():
+    """The host side of wm_resize_tiles_u8 (survey.pil_bilinear_coeffs, pure Python doubles) computes Pillow's integers."""
+    from wildlifemapper_b200.survey import pil_bilinear_coeffs
+    for n_in, n_out in [(1024, 768), (900, 768), (240, 614), (17, 3), (5, 5), (1000, 999)]:
+        b, k = pil_bilinear_coeffs(n_in, n_out)
+        ob, ok = of.pil_bilinear_coeffs(n_in, n_out)
+        np.testing.assert_array_equal(np.array(b, np.int32), ob)
+        np.testing.assert_array_equal(np.array(k, np.int32), ok)

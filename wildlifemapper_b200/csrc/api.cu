@@ -29,6 +29,8 @@ int tiles_from_u8_launch(const uint8_t*, int, int, long long, const int*, int, i
 int merge_detections_launch(const float*, const int*, const int*, int, int, float, int*, float*, float*, long long*, int*,
                             int*, cudaStream_t);
 int coco_pack_launch(const float*, const float*, const long long*, const long long*, int, float*, long long*, cudaStream_t);
+int resize_u8_launch(const uint8_t*, long long, const int*, int, int, int, uint8_t*, uint8_t*, int, int, const int*, const int*,
+                     int, const int*, const int*, int, cudaStream_t);
 }  // namespace wm
 
 namespace {
@@ -214,6 +216,11 @@ int wm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const f
     }
   }
   return check_launch(wm::gemm_dispatch(ta, tw, tc16, tc32, p, bn, t_num_sms, (cudaStream_t)stream), "wm_gemm_bf16");
+}
+
+int wm_num_sms(void) {
+  if (int rc = ensure_device()) return rc;
+  return t_num_sms;
 }
 
 int wm_conv3x3_nhwc_bf16(const void* X, const void* W, void* out_bf16, float* out_f32, int B, int C, int N,
@@ -434,6 +441,21 @@ int wm_tiles_from_u8(const uint8_t* img, int H, int W, int64_t row_stride, const
   return check_launch(wm::tiles_from_u8_launch(img, H, W, row_stride, origins, T, content_h, content_w, mean3, std3, out,
                                                (cudaStream_t)stream),
                       "wm_tiles_from_u8");
+}
+
+int wm_resize_tiles_u8(const uint8_t* img, int img_h, int img_w, int64_t row_stride, const int32_t* origins, int T, int tile_h,
+                       int tile_w, uint8_t* tmp, uint8_t* out, int out_h, int out_w, const int32_t* xbounds, const int32_t* xk,
+                       int xksize, const int32_t* ybounds, const int32_t* yk, int yksize, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (T < 0 || T > 65535 || img_h <= 0 || img_w <= 0 || tile_h <= 0 || tile_w <= 0 || tile_h > 65535 || out_h <= 0 ||
+      out_w <= 0 || out_h > 65535 || tile_h > img_h || tile_w > img_w || row_stride < (int64_t)img_w * 3 || xksize <= 0 || yksize <= 0)
+    return fail(WM_ERR_SHAPE, "wm_resize_tiles_u8: bad shape (tiles must lie inside the image)");
+  if (T > 0 && (img == nullptr || origins == nullptr || tmp == nullptr || out == nullptr || xbounds == nullptr || xk == nullptr ||
+                ybounds == nullptr || yk == nullptr))
+    return fail(WM_ERR_SHAPE, "wm_resize_tiles_u8: null pointer");
+  return check_launch(wm::resize_u8_launch(img, row_stride, origins, T, tile_h, tile_w, tmp, out, out_h, out_w, xbounds, xk, xksize,
+                                           ybounds, yk, yksize, (cudaStream_t)stream),
+                      "wm_resize_tiles_u8");
 }
 
 int wm_merge_detections(const float* packed, const int32_t* counts, const int32_t* origins, int T, int Q, float score_thr,

@@ -530,22 +530,31 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const __nv_bfloat16* __re
     // ---- P V: 16 keys per k-step; the accumulators of n8 tiles 2 kk and 2 kk + 1 ARE the A fragment of k-step kk
 #pragma unroll
     for (int kk = 0; kk < KT / 16; ++kk) {
-      uint32_t pa[4];
-      float e[8];
+      // P is split into two bf16 terms (hi + lo, 16 mantissa bits): the thread-per-query kernel this one replaces kept P in
+      // fp32, and a single bf16 rounding of P moved the full-size ViT-H box error to the edge of its gate (mean L1 1.02e-3
+      // vs 1e-3).  Two MMAs per fragment instead of one: nothing for 3.5 GFLOP.
+      uint32_t pa[4], pl[4];
+      float e[8], el[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         e[u] = ex2_approx(sc[2 * kk + (u >> 2)][u & 3] - mx[(u >> 1) & 1]);  // masked keys: exp2(-inf) = 0
         l_run[(u >> 1) & 1] += e[u];
+        el[u] = e[u] - __bfloat162float(__float2bfloat16_rn(e[u]));
       }
       pa[0] = pack_bf16(e[0], e[1]);  // row g,     keys 16 kk + 2 t4, +1
       pa[1] = pack_bf16(e[2], e[3]);  // row g + 8
       pa[2] = pack_bf16(e[4], e[5]);  // row g,     keys 16 kk + 8 + 2 t4, +1
       pa[3] = pack_bf16(e[6], e[7]);  // row g + 8
+      pl[0] = pack_bf16(el[0], el[1]);
+      pl[1] = pack_bf16(el[2], el[3]);
+      pl[2] = pack_bf16(el[4], el[5]);
+      pl[3] = pack_bf16(el[6], el[7]);
 #pragma unroll
       for (int i = 0; i < HD / 8; ++i) {
         uint32_t b0, b1;  // B[k = key][n = dim] = V[key][dim]: two transposed 8 x 8 tiles (keys 16 kk .. +7, +8 .. +15)
         ldmatrix_x2_trans(b0, b1, smem_u32(sV + (16 * kk + (lane & 15)) * ROWB + i * 16));
         mma_bf16_16816(o[i], pa, b0, b1);
+        mma_bf16_16816(o[i], pl, b0, b1);
       }
     }
   }

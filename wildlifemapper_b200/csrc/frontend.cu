@@ -9,6 +9,10 @@
 //   merge_count/compact      per-tile packed rows -> one image-level candidate list (score filter of
 //                            visualize_prediction.py:150, boxes moved by the tile origin), tile-major, query order
 //                            preserved (a stable compaction), ready for the per-class wm_nms.
+//   resize_u8_pass_kernel    the PIL bilinear (antialiased) resize behind `RandomResize([768], max_size=768)`
+//                            (dataloader_coco.py:275-292 -> utils/augmentation.py:77-107 -> torchvision F.resize ->
+//                            PIL Image.resize(BILINEAR)) in PIL's own 8-bit fixed-point arithmetic: 22-bit integer
+//                            coefficients, horizontal pass into a uint8 intermediate, then the vertical pass -- bit-exact.
 //   coco_pack_kernel         `convert_to_xywh` + the per-detection record of `prepare_for_coco_detection`
 //                            (inference.py:149-171, 235-237) for the kept detections.
 #include <cuda_runtime.h>
@@ -157,6 +161,53 @@ int coco_pack_launch(const float* boxes, const float* scores, const long long* l
                      float* out_xywh_score, long long* out_cat, cudaStream_t st) {
   if (n_keep == 0) return WM_OK;
   coco_pack_kernel<<<(n_keep + 255) / 256, 256, 0, st>>>(boxes, scores, labels, keep, n_keep, out_xywh_score, out_cat);
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+
+// ------------------------------------------------------------------ PIL-exact bilinear resize of uint8 RGB tiles
+// One pass of ImagingResample for 8-bit pixels (Pillow src/libImaging/Resample.c, ImagingResampleHorizontal_8bpc /
+// ImagingResampleVertical_8bpc): out = clip8((2^21 + sum_x in[xmin + x] * k[x]) >> 22), k = the precomputed 22-bit
+// coefficients of the output position (computed on the host in double precision exactly as precompute_coeffs /
+// normalize_coeffs_8bpc do).  Thread = one output pixel (3 channels); blockIdx.z = tile.
+//   horizontal: in = tile window of the survey image (origin from `origins`), out[t][y][xo]
+//   vertical:   in = the horizontal pass's output [t][y][xo], out[t][yo][xo]
+__global__ void __launch_bounds__(256) resize_u8_pass_kernel(const uint8_t* __restrict__ in, long long in_row_stride,
+                                                             long long in_tile_stride, const int* __restrict__ origins,
+                                                             uint8_t* __restrict__ out, int out_w, int out_h,
+                                                             const int* __restrict__ bounds, const int* __restrict__ kk,
+                                                             int ksize, int vertical) {
+  const int xo = blockIdx.x * 256 + threadIdx.x, yo = blockIdx.y, t = blockIdx.z;
+  if (xo >= out_w) return;
+  const uint8_t* base = in + (long long)t * in_tile_stride;
+  if (origins) base += (long long)origins[2 * t] * in_row_stride + (long long)origins[2 * t + 1] * 3;
+  const int o = vertical ? yo : xo;
+  const int lo = bounds[2 * o], cnt = bounds[2 * o + 1];
+  const int* k = kk + (size_t)o * ksize;
+  int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+  for (int i = 0; i < cnt; ++i) {
+    const uint8_t* px = vertical ? base + (long long)(lo + i) * in_row_stride + (long long)xo * 3
+                                 : base + (long long)yo * in_row_stride + (long long)(lo + i) * 3;
+    const int w = __ldg(k + i);
+    s0 += (int)__ldg(px) * w;
+    s1 += (int)__ldg(px + 1) * w;
+    s2 += (int)__ldg(px + 2) * w;
+  }
+  uint8_t* q = out + (((size_t)t * out_h + yo) * out_w + xo) * 3;
+  q[0] = (uint8_t)min(max(s0 >> 22, 0), 255);
+  q[1] = (uint8_t)min(max(s1 >> 22, 0), 255);
+  q[2] = (uint8_t)min(max(s2 >> 22, 0), 255);
+}
+
+int resize_u8_launch(const uint8_t* img, long long row_stride, const int* origins, int T, int H, int W, uint8_t* tmp,
+                     uint8_t* out, int oh, int ow, const int* xbounds, const int* xk, int xks, const int* ybounds,
+                     const int* yk, int yks, cudaStream_t st) {
+  if (T == 0) return WM_OK;
+  (void)W;
+  // horizontal: [T, H, ow] from the image windows;  vertical: [T, oh, ow] from the intermediate
+  resize_u8_pass_kernel<<<dim3((ow + 255) / 256, H, T), 256, 0, st>>>(img, row_stride, 0, origins, tmp, ow, H, xbounds, xk, xks, 0);
+  resize_u8_pass_kernel<<<dim3((ow + 255) / 256, oh, T), 256, 0, st>>>(tmp, (long long)ow * 3, (long long)H * ow * 3, nullptr, out, ow,
+                                                                       oh, ybounds, yk, yks, 1);
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 

@@ -202,20 +202,27 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   mask[(size_t)i * nblk + col_blk] = bits;
 }
 
-// One block: walk the sorted boxes 64 at a time; warp 0 lane 0 resolves the in-block chain from the diagonal
-// words, then all threads OR the rows of the survivors into the running "removed" bitmap.
-__global__ void __launch_bounds__(256) nms_reduce_kernel(const unsigned long long* __restrict__ mask,
-                                                         const int* __restrict__ order, int n,
-                                                         long long* __restrict__ keep, int* __restrict__ num_keep) {
+// One block of 1024 threads walks the sorted boxes 64 at a time:
+//   A  64 threads fetch the block's diagonal mask words into shared memory (one coalesced-latency round trip instead of
+//      64 dependent global loads in the serial chain below: that chain was 5.4 ms of latency for 10 k boxes);
+//   B  one thread resolves the in-block greedy chain from shared memory / registers and appends the survivors;
+//   C  all threads OR the mask rows of the survivors into the running "removed" bitmap: thread = (16-row group, word),
+//      16 independent predicated loads each, merged with a shared-memory atomicOr.
+__global__ void __launch_bounds__(1024) nms_reduce_kernel(const unsigned long long* __restrict__ mask,
+                                                          const int* __restrict__ order, int n,
+                                                          long long* __restrict__ keep, int* __restrict__ num_keep) {
   extern __shared__ unsigned long long removed[];  // nblk words
+  __shared__ unsigned long long diag[64];
   __shared__ unsigned long long alive_word;
   __shared__ int kept_total;
   const int nblk = (n + 63) / 64;
-  for (int w = threadIdx.x; w < nblk; w += 256) removed[w] = 0;
+  for (int w = threadIdx.x; w < nblk; w += 1024) removed[w] = 0;
   if (threadIdx.x == 0) kept_total = 0;
   __syncthreads();
   for (int blk = 0; blk < nblk; ++blk) {
     const int cnt = min(64, n - blk * 64);
+    if (threadIdx.x < 64) diag[threadIdx.x] = threadIdx.x < cnt ? mask[(size_t)(blk * 64 + threadIdx.x) * nblk + blk] : 0ull;
+    __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long rem = removed[blk];
       unsigned long long alive = 0;
@@ -224,7 +231,7 @@ __global__ void __launch_bounds__(256) nms_reduce_kernel(const unsigned long lon
         if (!((rem >> t) & 1ull)) {
           alive |= 1ull << t;
           keep[kt++] = order[blk * 64 + t];
-          rem |= mask[(size_t)(blk * 64 + t) * nblk + blk];
+          rem |= diag[t];
         }
       }
       alive_word = alive;
@@ -232,15 +239,19 @@ __global__ void __launch_bounds__(256) nms_reduce_kernel(const unsigned long lon
     }
     __syncthreads();
     const unsigned long long alive = alive_word;
-    for (int w = blk + 1 + threadIdx.x; w < nblk; w += 256) {
-      unsigned long long acc = removed[w];
-      unsigned long long a = alive;
-      while (a) {
-        const int t = __ffsll((long long)a) - 1;
-        a &= a - 1;
-        acc |= mask[(size_t)(blk * 64 + t) * nblk + w];
+    const int nw = nblk - blk - 1;
+    for (int idx = threadIdx.x; idx < 4 * nw; idx += 1024) {
+      const int grp = idx / nw, w = blk + 1 + idx % nw;  // consecutive threads: consecutive words of the same rows
+      const unsigned long long a16 = (alive >> (16 * grp)) & 0xffffull;
+      if (a16 == 0) continue;
+      const unsigned long long* mrow = mask + (size_t)(blk * 64 + 16 * grp) * nblk + w;
+      unsigned long long acc = 0;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const unsigned long long m = (16 * grp + t < cnt) ? mrow[(size_t)t * nblk] : 0ull;  // independent loads
+        acc |= ((a16 >> t) & 1ull) ? m : 0ull;
       }
-      removed[w] = acc;
+      if (acc) atomicOr(&removed[w], acc);
     }
     __syncthreads();
   }
@@ -256,7 +267,7 @@ int nms_launch(const float* boxes, const float* scores, const long long* labels,
   const int nblk = (n + 63) / 64;
   rank_desc_kernel<<<dim3((n + 255) / 256, 1), 256, 0, st>>>(scores, n, order_ws, 0, 0);
   nms_mask_kernel<<<dim3(nblk, nblk), 64, 0, st>>>(boxes, order_ws, labels, n, thr, mask_ws);
-  nms_reduce_kernel<<<1, 256, nblk * sizeof(unsigned long long), st>>>(mask_ws, order_ws, n, keep, num_keep);
+  nms_reduce_kernel<<<1, 1024, nblk * sizeof(unsigned long long), st>>>(mask_ws, order_ws, n, keep, num_keep);
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 

@@ -25,6 +25,7 @@ SIGNATURES = {
     "wm_debug_flash_trace": [_p],
     "wm_debug_window_trace": [_p],
     "wm_gemm_bf16": [_p, _i64, _p, _i64, _p, _p, _i64, _i, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _p],
+    "wm_num_sms": [],
     "wm_conv3x3_nhwc_bf16": [_p, _p, _p, _p, _i, _i, _i, _p],
     "wm_layernorm": [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _f, _p],
     "wm_patchify": [_p, _p, _p, _i, _i, _p],
@@ -40,6 +41,7 @@ SIGNATURES = {
     "wm_nms": [_p, _p, _p, _i, _d, _p, _p, _p, _p, _p],
     "wm_nms_batched": [_p, _p, _i, _i, _f, _d, _i, _p, _p, _p],
     "wm_tiles_from_u8": [_p, _i, _i, _i64, _p, _i, _i, _i, _p, _p, _p, _p],
+    "wm_resize_tiles_u8": [_p, _i, _i, _i64, _p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _p, _i, _p],
     "wm_merge_detections": [_p, _p, _p, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p],
     "wm_pack_coco": [_p, _p, _p, _p, _i, _p, _p, _p],
 }

@@ -274,6 +274,26 @@ _define("tiles_from_u8(Tensor img, Tensor origins, int content_h, int content_w,
         "Tensor(a!) out) -> ()", _tiles_from_u8)
 
 
+def _resize_tiles_u8(img, origins, tile_h, tile_w, tmp, out, xbounds, xk, ybounds, yk):
+    _chk(img, torch.uint8, "resize_tiles_u8.img"); _chk(origins, torch.int32, "resize_tiles_u8.origins")
+    _chk(tmp, torch.uint8, "resize_tiles_u8.tmp"); _chk(out, torch.uint8, "resize_tiles_u8.out")
+    for t, n in ((xbounds, "xbounds"), (xk, "xk"), (ybounds, "ybounds"), (yk, "yk")):
+        _chk(t, torch.int32, "resize_tiles_u8." + n)
+        assert t.is_contiguous()
+    H, W, three = img.shape
+    T, oh, ow, _ = out.shape
+    assert three == 3 and img.stride(1) == 3 and origins.is_contiguous() and origins.shape[0] == T
+    assert out.is_contiguous() and tmp.is_contiguous() and tmp.numel() >= T * tile_h * ow * 3
+    assert tuple(xbounds.shape) == (ow, 2) and xk.shape[0] == ow and tuple(ybounds.shape) == (oh, 2) and yk.shape[0] == oh
+    _lib.call("wm_resize_tiles_u8", img.data_ptr(), H, W, img.stride(0), origins.data_ptr(), T, int(tile_h), int(tile_w),
+              tmp.data_ptr(), out.data_ptr(), oh, ow, xbounds.data_ptr(), xk.data_ptr(), xk.shape[1], ybounds.data_ptr(),
+              yk.data_ptr(), yk.shape[1], _stream())
+
+
+_define("resize_tiles_u8(Tensor img, Tensor origins, int tile_h, int tile_w, Tensor(a!) tmp, Tensor(b!) out, Tensor xbounds, "
+        "Tensor xk, Tensor ybounds, Tensor yk) -> ()", _resize_tiles_u8)
+
+
 def _merge_detections(packed, counts, origins, score_thr, tile_n_ws, boxes, scores, labels, src, total):
     _chk(packed, torch.float32, "merge_detections.packed"); _chk(counts, torch.int32, "merge_detections.counts")
     _chk(origins, torch.int32, "merge_detections.origins"); _chk(tile_n_ws, torch.int32, "merge_detections.tile_n_ws")

@@ -322,7 +322,8 @@ int wm_attn_flash(const void* q, int64_t q_rows, int64_t q_width, int64_t ldq, i
   // head dim 64 with rel-pos (encoder global blocks of ViT-B / ViT-L): v7 (ring of three score buffers, cheap prologue,
   // deferred publication of P: 2.29 vs 2.74 ms per launch at batch 32).  Head dims 80 / 128 (ViT-H, HFC cross-attention)
   // and the bias-free head-padded decoder attention: v4 (v7 without rel-pos measured 10 % slower per step than v4).
-  if (hd == 64 && rel_table != nullptr && g_flash_version.load() == 7)
+  const int fv = g_flash_version.load();
+  if (hd == 64 && rel_table != nullptr && fv == 7)
     return check_launch(wm::flash7_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v7)");
   return check_launch(wm::flash4_dispatch(tq, tk, tv, trel, p, hd, (cudaStream_t)stream), "wm_attn_flash(v4)");
 }

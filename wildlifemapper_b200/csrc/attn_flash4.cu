@@ -62,6 +62,14 @@ __device__ __forceinline__ float ex2_poly(float x) {
 #define WM_F4_POLY 6
 #endif
 
+// one stage of the lane-dependent down-shift of x[0 .. 64 + SH - 1): lanes with bit SH set take x[i + SH]
+template <int SH>
+__device__ __forceinline__ void f4_barrel_stage(uint32_t (&x)[96], int lane) {
+  const bool on = (lane & SH) != 0;
+#pragma unroll
+  for (int i = 0; i < 64 + SH - 1; ++i) x[i] = on ? x[i + SH] : x[i];  // ascending i: x[i + SH] is still the old value
+}
+
 constexpr int F4_THREADS = 384;
 constexpr float F4_LOG2E = 1.4426950408889634f;
 constexpr float F4_TAU = 16.0f;  // lazy-rescale threshold (log2 units): p <= 2^16 between rescales (bf16 P and the fp32 accumulators have the range)
@@ -78,8 +86,7 @@ struct Flash4Cfg {
   static constexpr int OFF_Q = 0;                  // 2 query tiles
   static constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * TILE_BYTES;
-  // RELPOS prologue: Rw [128 rows] + 2 x Rh slice [80 rows] (x SUB sub-tiles); afterwards its first 32 KB are fp32
-  // scatter scratch.  Head dim 64: own region.  Larger head dims: the tables ALIAS K stage 1 and the V stages, whose
+  // RELPOS prologue: Rw [128 rows] + 2 x Rh slice [80 rows] (x SUB sub-tiles).  Head dim 64: own region.  Larger head dims: the tables ALIAS K stage 1 and the V stages, whose
   // first loads wait for the prologue (t_done).
   static constexpr bool TAB_ALIAS = RELPOS && SUB > 1;
   static constexpr int TAB_BYTES = RELPOS ? SUB * (16384 + 2 * 10240) : 0;
@@ -367,27 +374,30 @@ flash4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         tmem_ld_wait();
         bh64 = __uint_as_float(x) * F4_LOG2E;
       }
-      // bias_w[kw] = T_w[qj + 63 - kw]: per-thread scatter through a private XOR-swizzled 32-float smem row
-      float* scr = reinterpret_cast<float*>(smem + Cfg::OFF_TAB) + ((t * 128 + r) << 5);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld32(s_addr + c * 32, v);
+      // bias_w[kw] = T_w[qj + 63 - kw], qj = (q4 & 1) * 32 + lane: every lane needs a 64-column window of its T_w row that
+      // starts at a lane-dependent column.  Load the 96 columns [base, base + 96) (base = 32 (q4 & 1), warp-uniform) and
+      // shift them down by `lane` positions with a barrel of selects (5 stages, 346 SEL).  (Round 1 scattered through a
+      // shared-memory scratch with ~10 instructions per examined column: 10 us of every CTA's 67, attn_flash7.cu.)
+      {
+        (void)qj;
+        const uint32_t base = (uint32_t)(q4 & 1) * 32u;
+        uint32_t x[96];
+        {
+          uint32_t x0[32], x1[32], x2[32];
+          tmem_ld32(s_addr + base, x0);
+          tmem_ld32(s_addr + base + 32, x1);
+          tmem_ld32(s_addr + base + 64, x2);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kw = qj + 63 - (c * 32 + i) - half * 32;
-            if (kw >= 0 && kw < 32) scr[((((kw >> 2) ^ (r & 7)) << 2) | (kw & 3))] = __uint_as_float(v[i]) * F4_LOG2E;
-          }
+          for (int i = 0; i < 32; ++i) { x[i] = x0[i]; x[32 + i] = x1[i]; x[64 + i] = x2[i]; }
         }
+        f4_barrel_stage<16>(x, lane);
+        f4_barrel_stage<8>(x, lane);
+        f4_barrel_stage<4>(x, lane);
+        f4_barrel_stage<2>(x, lane);
+        f4_barrel_stage<1>(x, lane);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 w = *reinterpret_cast<const float4*>(scr + ((g ^ (r & 7)) << 2));
-          tw[half * 32 + 4 * g] = w.x; tw[half * 32 + 4 * g + 1] = w.y;
-          tw[half * 32 + 4 * g + 2] = w.z; tw[half * 32 + 4 * g + 3] = w.w;
-        }
+        for (int kw = 0; kw < 64; ++kw) tw[RELPOS ? kw : 0] = __uint_as_float(x[63 - kw]) * F4_LOG2E;  // x[i] = T_w[qj + i]
       }
       tc_fence_before();
       __syncwarp();

@@ -240,6 +240,8 @@ class Ctx:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        # torchrun exports OMP_NUM_THREADS=1: the random initialisation of the models on the host would take minutes
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(1, self.world)))
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:

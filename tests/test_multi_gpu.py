@@ -49,6 +49,12 @@ def _worker(rank, world, port, B, q):
             n, k = int(counts[b]), int(kcnt[b])
             ok = ok and torch.equal(gathered[0][b, :n], ref[0][b, :n]) and torch.equal(gathered[2][b, :k], ref[2][b, :k])
         q.put((bool(ok), int(counts.sum()), int(kcnt.sum())))
+        del single
+    # the captured graphs hold NCCL work: release them before the process group goes away
+    del det
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,9 +70,12 @@ def test_two_rank_gather_equals_single_gpu_run():
         p.start()
     ok, n_det, n_keep = q.get(timeout=600)
     for p in procs:
-        p.join(120)
-    assert all(p.exitcode == 0 for p in procs)
+        p.join(60)
+    hung = [p for p in procs if p.exitcode is None]
+    for p in hung:  # never leave a rank behind on the GPU box
+        p.kill()
     assert ok and n_det > 0 and n_keep > 0
+    assert not hung and all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
 
 
 def test_model_on_second_device_while_first_is_current():

@@ -180,6 +180,24 @@ int wm_merge_detections(const float* packed, const int32_t* counts, const int32_
 int wm_pack_coco(const float* boxes, const float* scores, const int64_t* labels, const int64_t* keep, int n_keep,
                  float* out_xywh_score, int64_t* out_category, void* stream);
 
+/* ---- evaluation-time criterion: inference.py:29-89 evaluate() calls criterion(outputs, targets) ---- */
+
+/* Matching cost of HungarianMatcher.forward (modeling/matcher.py:58-73) for ALL targets of the batch at once:
+ * cost[r, t] = w_bbox * L1(boxes[r], tgt_boxes[t]) + w_class * (-softmax(logits[r])[tgt_ids[t]])
+ *              + w_giou * (-GIoU(xyxy(boxes[r]), xyxy(tgt_boxes[t]))),  r = b * Q + q in [0, rows), t in [0, T).
+ * logits fp32 [rows, C1], boxes fp32 [rows, 4] (cxcywh), tgt_ids int64 [T], tgt_boxes fp32 [T, 4], cost fp32 [rows, T].
+ * The per-image linear_sum_assignment on the diagonal blocks stays on the host (scipy), as in the reference. */
+int wm_match_cost(const float* logits, const float* boxes, const int64_t* tgt_ids, const float* tgt_boxes, int rows, int T,
+                  int C1, float w_class, float w_bbox, float w_giou, float* cost, void* stream);
+
+/* SetCriterion losses (build_sam.py:95-150) given the matching: m_row int32 [n_match] = b * Q + q of every matched query,
+ * m_label int64 / m_box fp32 [n_match(,4)] its target, tgt_len int32 [B] targets per image, empty_weight fp32 [C1]
+ * (1, ..., 1, eos_coef), num_boxes the normaliser (clamped, all-reduced by the caller).  tcls_ws int32 [B*Q] scratch.
+ * out5 fp32 [5] = loss_ce, class_error, cardinality_error, loss_bbox, loss_giou.  Forward values only. */
+int wm_set_criterion(const float* logits, const float* boxes, const int32_t* m_row, const int64_t* m_label, const float* m_box,
+                     int n_match, const int32_t* tgt_len, const float* empty_weight, int B, int Q, int C1, float num_boxes,
+                     int32_t* tcls_ws, float* out5, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

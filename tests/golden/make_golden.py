@@ -205,11 +205,46 @@ def golden_frontend() -> None:
     print("wrote golden_frontend", {k: (v.shape if v.ndim else str(v)[:16]) for k, v in res.items()})
 
 
+def golden_criterion() -> None:
+    """The reference's own HungarianMatcher + SetCriterion (build through sam_model_registry's args path) on seeded cases."""
+    sys.path.insert(0, REF)
+    from segment_anything.build_sam import SetCriterion
+    from segment_anything.modeling.matcher import HungarianMatcher
+    from oracle.criterion import CRITERION_CASES, make_case
+    matcher = HungarianMatcher(cost_class=1, cost_bbox=5, cost_giou=2)  # train.py defaults: set_cost_class / bbox / giou
+    crit = SetCriterion(7, matcher=matcher, weight_dict={"loss_ce": 3, "loss_bbox": 5, "loss_giou": 2}, eos_coef=0.1,
+                        losses=["labels", "boxes", "cardinality"]).eval()
+    res = {}
+    for tag, B, Q, sizes in CRITERION_CASES:
+        logits, boxes, targets = make_case(tag, B, Q, sizes)
+        out = {"pred_logits": torch.from_numpy(logits), "pred_boxes": torch.from_numpy(boxes)}
+        tg = [{"labels": torch.from_numpy(t["labels"]), "boxes": torch.from_numpy(t["boxes"])} for t in targets]
+        with torch.no_grad():
+            idx = matcher(out, tg)
+            losses = crit(out, tg)
+        for i, (a, b) in enumerate(idx):
+            res[f"{tag}.idx{i}.src"], res[f"{tag}.idx{i}.tgt"] = a.numpy(), b.numpy()
+        for k, v in losses.items():
+            res[f"{tag}.{k}"] = np.array(float(v), np.float64)
+        if sum(sizes):
+            ids = torch.cat([t["labels"] for t in tg]); tb = torch.cat([t["boxes"] for t in tg])
+            prob = out["pred_logits"].flatten(0, 1).softmax(-1)
+            from segment_anything.utils.box_ops import box_cxcywh_to_xyxy, generalized_box_iou
+            C = 5 * torch.cdist(out["pred_boxes"].flatten(0, 1), tb, p=1) + 1 * (-prob[:, ids]) + 2 * (-generalized_box_iou(
+                box_cxcywh_to_xyxy(out["pred_boxes"].flatten(0, 1)), box_cxcywh_to_xyxy(tb)))
+            c = C.numpy().reshape(-1)
+            res[f"{tag}.cost.samples"] = c[sample_positions(c.size, tag + ".cost")]
+    np.savez_compressed(os.path.join(HERE, "golden_criterion.npz"), **res)
+    print("wrote golden_criterion", sorted(k for k in res if "idx" not in k))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 8)
-    which = sys.argv[1:] or ["post", "nms", "frontend", "vit_t", "vit_t900", "vit_b"]
+    which = sys.argv[1:] or ["post", "nms", "frontend", "criterion", "vit_t", "vit_t900", "vit_b"]
     if "frontend" in which:
         golden_frontend()
+    if "criterion" in which:
+        golden_criterion()
     if "post" in which:
         golden_post()
     if "nms" in which:

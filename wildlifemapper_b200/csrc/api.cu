@@ -29,6 +29,10 @@ int tiles_from_u8_launch(const uint8_t*, int, int, long long, const int*, int, i
 int merge_detections_launch(const float*, const int*, const int*, int, int, float, int*, float*, float*, long long*, int*,
                             int*, cudaStream_t);
 int coco_pack_launch(const float*, const float*, const long long*, const long long*, int, float*, long long*, cudaStream_t);
+int match_cost_launch(const float*, const float*, const long long*, const float*, int, int, int, float, float, float, float*,
+                      cudaStream_t);
+int criterion_launch(const float*, const float*, const int*, const long long*, const float*, int, const int*, const float*, int,
+                     int, int, float, int*, float*, cudaStream_t);
 int resize_u8_launch(const uint8_t*, long long, const int*, int, int, int, uint8_t*, uint8_t*, int, int, const int*, const int*,
                      int, const int*, const int*, int, cudaStream_t);
 }  // namespace wm
@@ -468,6 +472,31 @@ int wm_merge_detections(const float* packed, const int32_t* counts, const int32_
   return check_launch(wm::merge_detections_launch(packed, counts, origins, T, Q, score_thr, tile_n_ws, boxes, scores,
                                                   reinterpret_cast<long long*>(labels), src, total, (cudaStream_t)stream),
                       "wm_merge_detections");
+}
+
+int wm_match_cost(const float* logits, const float* boxes, const int64_t* tgt_ids, const float* tgt_boxes, int rows, int T,
+                  int C1, float w_class, float w_bbox, float w_giou, float* cost, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (rows < 0 || T < 0 || C1 < 2 || C1 > 64) return fail(WM_ERR_SHAPE, "wm_match_cost: bad shape rows=%d T=%d C1=%d", rows, T, C1);
+  if ((long long)rows * T > 0 && (logits == nullptr || boxes == nullptr || tgt_ids == nullptr || tgt_boxes == nullptr || cost == nullptr))
+    return fail(WM_ERR_SHAPE, "wm_match_cost: null pointer");
+  return check_launch(wm::match_cost_launch(logits, boxes, reinterpret_cast<const long long*>(tgt_ids), tgt_boxes, rows, T, C1,
+                                            w_class, w_bbox, w_giou, cost, (cudaStream_t)stream),
+                      "wm_match_cost");
+}
+
+int wm_set_criterion(const float* logits, const float* boxes, const int32_t* m_row, const int64_t* m_label, const float* m_box,
+                     int n_match, const int32_t* tgt_len, const float* empty_weight, int B, int Q, int C1, float num_boxes,
+                     int32_t* tcls_ws, float* out5, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (B <= 0 || Q <= 0 || C1 < 2 || C1 > 64 || n_match < 0 || !(num_boxes > 0.0f))
+    return fail(WM_ERR_SHAPE, "wm_set_criterion: bad shape B=%d Q=%d C1=%d n_match=%d num_boxes=%f", B, Q, C1, n_match, num_boxes);
+  if (logits == nullptr || boxes == nullptr || tgt_len == nullptr || empty_weight == nullptr || tcls_ws == nullptr || out5 == nullptr ||
+      (n_match > 0 && (m_row == nullptr || m_label == nullptr || m_box == nullptr)))
+    return fail(WM_ERR_SHAPE, "wm_set_criterion: null pointer");
+  return check_launch(wm::criterion_launch(logits, boxes, m_row, reinterpret_cast<const long long*>(m_label), m_box, n_match,
+                                           tgt_len, empty_weight, B, Q, C1, num_boxes, tcls_ws, out5, (cudaStream_t)stream),
+                      "wm_set_criterion");
 }
 
 int wm_pack_coco(const float* boxes, const float* scores, const int64_t* labels, const int64_t* keep, int n_keep,

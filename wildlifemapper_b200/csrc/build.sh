@@ -8,7 +8,7 @@ BUILD=${WM_BUILD_DIR:-build}
 LIBNAME=${WM_LIB_NAME:-libwm_b200.so}
 mkdir -p $BUILD
 pids=()
-SRCS="gemm attn_flash4 attn_flash7 attn_window2 attn_window3 elementwise postprocess frontend api"
+SRCS="gemm attn_flash4 attn_flash7 attn_window2 attn_window3 elementwise postprocess frontend criterion api"
 for f in $SRCS; do
   if [ ! -f $BUILD/$f.o ] || [ $f.cu -nt $BUILD/$f.o ] || [ common.cuh -nt $BUILD/$f.o ] || [ wm_internal.h -nt $BUILD/$f.o ] || [ ../../include/wm_b200.h -nt $BUILD/$f.o ]; then
     $NVCC $FLAGS -Xptxas -v -c $f.cu -o $BUILD/$f.o > $BUILD/$f.log 2>&1 &

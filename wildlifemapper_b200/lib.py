@@ -43,6 +43,8 @@ SIGNATURES = {
     "wm_tiles_from_u8": [_p, _i, _i, _i64, _p, _i, _i, _i, _p, _p, _p, _p],
     "wm_resize_tiles_u8": [_p, _i, _i, _i64, _p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _p, _i, _p],
     "wm_merge_detections": [_p, _p, _p, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p],
+    "wm_match_cost": [_p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _p],
+    "wm_set_criterion": [_p, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _f, _p, _p, _p],
     "wm_pack_coco": [_p, _p, _p, _p, _i, _p, _p, _p],
 }
 

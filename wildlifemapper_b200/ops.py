@@ -328,4 +328,40 @@ def _pack_coco(boxes, scores, labels, keep, n_keep, out_xywh_score, out_category
 _define("pack_coco(Tensor boxes, Tensor scores, Tensor labels, Tensor? keep, int n_keep, Tensor(a!) out_xywh_score, "
         "Tensor(b!) out_category) -> ()", _pack_coco)
 
+# ------------------------------------------------------------------ evaluation-time criterion (section 8f row 4)
+def _match_cost(logits, boxes, tgt_ids, tgt_boxes, w_class, w_bbox, w_giou, cost):
+    _chk(logits, torch.float32, "match_cost.logits"); _chk(boxes, torch.float32, "match_cost.boxes")
+    _chk(tgt_ids, torch.int64, "match_cost.tgt_ids"); _chk(tgt_boxes, torch.float32, "match_cost.tgt_boxes")
+    _chk(cost, torch.float32, "match_cost.cost")
+    rows, C1 = logits.shape
+    T = tgt_ids.shape[0]
+    assert logits.is_contiguous() and boxes.is_contiguous() and tgt_boxes.is_contiguous() and cost.is_contiguous()
+    assert tuple(boxes.shape) == (rows, 4) and tuple(tgt_boxes.shape) == (T, 4) and tuple(cost.shape) == (rows, T)
+    _lib.call("wm_match_cost", logits.data_ptr(), boxes.data_ptr(), tgt_ids.data_ptr(), tgt_boxes.data_ptr(), rows, T, C1,
+              float(w_class), float(w_bbox), float(w_giou), cost.data_ptr(), _stream())
+
+
+_define("match_cost(Tensor logits, Tensor boxes, Tensor tgt_ids, Tensor tgt_boxes, float w_class, float w_bbox, float w_giou, "
+        "Tensor(a!) cost) -> ()", _match_cost)
+
+
+def _set_criterion(logits, boxes, m_row, m_label, m_box, tgt_len, empty_weight, num_boxes, tcls_ws, out5):
+    _chk(logits, torch.float32, "set_criterion.logits"); _chk(boxes, torch.float32, "set_criterion.boxes")
+    _chk(m_row, torch.int32, "set_criterion.m_row"); _chk(m_label, torch.int64, "set_criterion.m_label")
+    _chk(m_box, torch.float32, "set_criterion.m_box"); _chk(tgt_len, torch.int32, "set_criterion.tgt_len")
+    _chk(empty_weight, torch.float32, "set_criterion.empty_weight"); _chk(tcls_ws, torch.int32, "set_criterion.tcls_ws")
+    _chk(out5, torch.float32, "set_criterion.out5")
+    B, Q, C1 = logits.shape
+    n = m_row.shape[0]
+    assert logits.is_contiguous() and boxes.is_contiguous() and tuple(boxes.shape) == (B, Q, 4)
+    assert m_label.shape[0] == n and m_box.numel() == 4 * n and m_box.is_contiguous() and tgt_len.numel() == B
+    assert empty_weight.numel() == C1 and tcls_ws.numel() >= B * Q and out5.numel() == 5
+    _lib.call("wm_set_criterion", logits.data_ptr(), boxes.data_ptr(), m_row.data_ptr(), m_label.data_ptr(), m_box.data_ptr(), n,
+              tgt_len.data_ptr(), empty_weight.data_ptr(), B, Q, C1, float(num_boxes), tcls_ws.data_ptr(), out5.data_ptr(),
+              _stream())
+
+
+_define("set_criterion(Tensor logits, Tensor boxes, Tensor m_row, Tensor m_label, Tensor m_box, Tensor tgt_len, "
+        "Tensor empty_weight, float num_boxes, Tensor(a!) tcls_ws, Tensor(b!) out5) -> ()", _set_criterion)
+
 ops = torch.ops.wm_b200

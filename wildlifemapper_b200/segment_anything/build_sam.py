@@ -1,7 +1,6 @@
-"""Model factory, registry and PostProcess with the reference names and signatures (reference
-``segment_anything/build_sam.py``).  The DETR loss (SetCriterion / HungarianMatcher) is training-only and out of
-scope of the tile-detection hot path: the factory returns a placeholder criterion that raises
-when called."""
+"""Model factory, registry, SetCriterion and PostProcess with the reference names and signatures (reference
+``segment_anything/build_sam.py``).  The criterion computes the forward values the reference's evaluation loop logs
+(``inference.py:29-89``); its backward belongs to the training path, which is not implemented."""
 from functools import partial
 
 import torch
@@ -10,6 +9,7 @@ from torch import nn
 from wildlifemapper_b200 import postprocess as _pp
 
 from .modeling import ImageEncoderViT, MaskDecoder, PromptEncoder, Sam, TwoWayTransformer
+from .modeling.matcher import build_matcher
 
 
 def build_sam_vit_h(checkpoint=None, args=None):
@@ -36,17 +36,59 @@ sam_model_registry = {
 
 
 class SetCriterion(nn.Module):
-    """Placeholder with the reference's name: the Hungarian-matched DETR loss (build_sam.py:62-210, matcher.py)
-    is training-only; calling it raises."""
+    """The DETR criterion of the reference (build_sam.py:62-210) for the EVALUATION loop: ``inference.py:29-89 evaluate()``
+    calls ``criterion(outputs, targets)`` under ``torch.no_grad()`` for every batch.  Forward values only -- Hungarian
+    matching (cost kernel + scipy, like the reference), then one sm_100a kernel for the weighted cross entropy, class
+    error, cardinality error, L1 and GIoU box losses (``wm_set_criterion``).  Inputs that require grad raise: the
+    backward is the training path, which this package does not implement."""
 
-    def __init__(self, num_classes=7, matcher=None, weight_dict=None, eos_coef=0.1, losses=()):
+    def __init__(self, num_classes, matcher, weight_dict, eos_coef, losses):
         super().__init__()
         self.num_classes, self.matcher, self.eos_coef, self.losses = num_classes, matcher, eos_coef, list(losses)
         self.weight_dict = dict(weight_dict or {})
+        empty_weight = torch.ones(self.num_classes + 1)
+        empty_weight[-1] = self.eos_coef
+        self.register_buffer("empty_weight", empty_weight)
+        for name in self.losses:
+            if name not in ("labels", "boxes", "cardinality"):
+                raise NotImplementedError(f"do you really want to compute {name} loss?")
 
     def forward(self, outputs, targets):
-        raise NotImplementedError("SetCriterion (training loss) is outside the B200 inference hot path; "
-                                  "SURVEY.md section 8f lists it as a 'next' row")
+        """-> {'loss_ce', 'class_error', 'loss_bbox', 'loss_giou', 'cardinality_error'}: 0-dim fp32 tensors on the device."""
+        logits, boxes = outputs["pred_logits"], outputs["pred_boxes"]
+        if torch.is_grad_enabled() and (logits.requires_grad or boxes.requires_grad):
+            raise RuntimeError("SetCriterion: inputs require grad, but wildlifemapper_b200 implements the evaluation path only "
+                               "(no backward kernels). Run under torch.no_grad().")
+        if self.matcher is None:
+            raise RuntimeError("SetCriterion needs a matcher (sam_model_registry builds one from args.set_cost_*)")
+        if "aux_outputs" in outputs:
+            raise NotImplementedError("aux_outputs (aux_loss=True) are a training-only option")
+        from wildlifemapper_b200.ops import ops
+        from .utils.misc import get_world_size, is_dist_avail_and_initialized
+        dev = logits.device
+        B, Q, C1 = logits.shape
+        indices = self.matcher({"pred_logits": logits, "pred_boxes": boxes}, targets)
+        # matched pairs, image-major, in the matcher's order (== _get_src_permutation_idx, build_sam.py:152-156)
+        rows = torch.cat([src + i * Q for i, (src, _) in enumerate(indices)]).to(device=dev, dtype=torch.int32)
+        m_label = torch.cat([t["labels"].to(dev)[J.to(dev)] for t, (_, J) in zip(targets, indices)]).to(torch.int64).contiguous()
+        m_box = torch.cat([t["boxes"].to(dev)[J.to(dev)] for t, (_, J) in zip(targets, indices)]).float().reshape(-1, 4).contiguous()
+        tgt_len = torch.tensor([len(t["labels"]) for t in targets], device=dev, dtype=torch.int32)
+        num_boxes = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float, device=dev)
+        if is_dist_avail_and_initialized():
+            torch.distributed.all_reduce(num_boxes)
+        num_boxes = torch.clamp(num_boxes / get_world_size(), min=1).item()
+        out5 = torch.empty(5, device=dev, dtype=torch.float32)
+        tcls = torch.empty(B * Q, device=dev, dtype=torch.int32)
+        ops.set_criterion(logits.detach().float().contiguous(), boxes.detach().float().contiguous(), rows, m_label, m_box, tgt_len,
+                          self.empty_weight.to(device=dev, dtype=torch.float32), float(num_boxes), tcls, out5)
+        res = {}
+        if "labels" in self.losses:
+            res["loss_ce"], res["class_error"] = out5[0], out5[1]
+        if "boxes" in self.losses:
+            res["loss_bbox"], res["loss_giou"] = out5[3], out5[4]
+        if "cardinality" in self.losses:
+            res["cardinality_error"] = out5[2]
+        return res
 
 
 class PostProcess(nn.Module):
@@ -109,7 +151,8 @@ def _build_sam(encoder_embed_dim, encoder_depth, encoder_num_heads, encoder_glob
         sam.load_state_dict(state_dict, strict=False)
     weight_dict = {"loss_ce": 3, "loss_bbox": getattr(args, "bbox_loss_coef", 5),
                    "loss_giou": getattr(args, "giou_loss_coef", 2)}
-    criterion = SetCriterion(num_classes, matcher=None, weight_dict=weight_dict,
+    matcher = build_matcher(args) if args is not None and hasattr(args, "set_cost_class") else None
+    criterion = SetCriterion(num_classes, matcher=matcher, weight_dict=weight_dict,
                              eos_coef=getattr(args, "eos_coef", 0.1), losses=["labels", "boxes", "cardinality"])
     device = getattr(args, "device", None)
     if device is not None:

@@ -5,7 +5,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from wildlifemapper_b200.ops import ops
-B, H, hd = 32, 12, 64
+B, H, hd = (64, 16, 80) if len(sys.argv) > 1 and sys.argv[1] == "vit_h" else (32, 12, 64)  # ViT-H: head dim 80 (window3 kernel)
 D = H * hd
 out = torch.empty(B * 4096, D, device="cuda", dtype=torch.bfloat16)
 for sc in (0.05, 0.3, 1.0):

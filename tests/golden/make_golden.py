@@ -190,6 +190,25 @@ def golden_frontend() -> None:
         res[f"{tag}.shape"] = np.array(arr.shape[:2])
         res[f"{tag}.sha256"] = np.array(hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest())
         res[f"{tag}.samples"] = arr.reshape(-1)[sample_positions(arr.size, tag)]
+    # the loader pipelines of dataloader_coco.py:275-292 on an image + target (boxes xyxy, area, center), incl. the train flip
+    import random
+    for tag, hw in (("pipe_sq", (1024, 1024)), ("pipe_wide", (600, 900))):
+        img = frontend_image(tag, hw)
+        g = torch.Generator().manual_seed(11)
+        xy = torch.rand(9, 2, generator=g) * torch.tensor([hw[1] - 80.0, hw[0] - 80.0])
+        wh = torch.rand(9, 2, generator=g) * 60 + 8
+        tgt = {"boxes": torch.cat([xy, xy + wh], 1), "area": wh[:, 0] * wh[:, 1], "center": xy + wh / 2,
+               "labels": torch.arange(9) % 6 + 1, "orig_size": torch.as_tensor([hw[0], hw[1]]), "size": torch.as_tensor([hw[0], hw[1]])}
+        for mode, tf in (("val", [T.RandomResize([768], max_size=768), T.ToTensor(), T.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])]),
+                         ("train", [T.RandomResize([768], max_size=768), T.ToTensor(), T.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225]),
+                                    T.FlipLR(fliplr=1.0)])):
+            random.seed(0)
+            im, tg = T.Compose(tf)(Image.fromarray(img), {k: v.clone() for k, v in tgt.items()})
+            a = im.numpy()
+            res[f"{tag}.{mode}.sha256"] = np.array(hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest())
+            res[f"{tag}.{mode}.shape"] = np.array(a.shape)
+            for k in ("boxes", "area", "center", "size"):
+                res[f"{tag}.{mode}.{k}"] = tg[k].numpy()
     # convert_to_xywh lives in inference.py, which does not import here (pycocotools): run its source text
     src = open(os.path.join(REF, "inference.py")).read()
     m = re.search(r"^def convert_to_xywh\(boxes\):\n(?:[ \t]+.*\n)+", src, re.M)

@@ -185,3 +185,34 @@ def test_plan_tiles_covers_image_with_overlap():
         plan_tiles(0, 10)
     with pytest.raises(ValueError):
         plan_tiles(10, 10, 1024, 1024)
+
+
+def test_loader_transforms_match_reference_goldens(golden_dir):
+    """The drop-in ``segment_anything.utils.augmentation`` (what dataloader_coco.py:275-292 composes) against goldens minted by
+    running the reference's own transform classes: image tensors sha256-exact, targets exact."""
+    import hashlib
+    import random
+    import sys as _sys
+    from PIL import Image
+    _sys.path.insert(0, os.path.join(ROOT, "wildlifemapper_b200"))
+    import segment_anything.utils.augmentation as T
+    from oracle.frontend import frontend_image
+    g = np.load(os.path.join(golden_dir, "golden_frontend.npz"))
+    for tag, hw in (("pipe_sq", (1024, 1024)), ("pipe_wide", (600, 900))):
+        img = frontend_image(tag, hw)
+        gen = torch.Generator().manual_seed(11)
+        xy = torch.rand(9, 2, generator=gen) * torch.tensor([hw[1] - 80.0, hw[0] - 80.0])
+        wh = torch.rand(9, 2, generator=gen) * 60 + 8
+        tgt = {"boxes": torch.cat([xy, xy + wh], 1), "area": wh[:, 0] * wh[:, 1], "center": xy + wh / 2,
+               "labels": torch.arange(9) % 6 + 1, "orig_size": torch.as_tensor([hw[0], hw[1]]), "size": torch.as_tensor([hw[0], hw[1]])}
+        norm = [T.RandomResize([768], max_size=768), T.ToTensor(), T.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])]
+        for mode, tf in (("val", norm), ("train", norm + [T.FlipLR(fliplr=1.0)])):
+            random.seed(0)
+            im, tg = T.Compose(tf)(Image.fromarray(img), {k: v.clone() for k, v in tgt.items()})
+            a = im.numpy()
+            assert tuple(a.shape) == tuple(g[f"{tag}.{mode}.shape"])
+            assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() == str(g[f"{tag}.{mode}.sha256"])
+            for k in ("boxes", "area", "center", "size"):
+                np.testing.assert_array_equal(tg[k].numpy(), g[f"{tag}.{mode}.{k}"], err_msg=f"{tag}.{mode}.{k}")
+    with pytest.raises(NotImplementedError):
+        T.RandomSizeCrop(384, 600)

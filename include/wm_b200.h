@@ -78,11 +78,19 @@ int wm_layernorm(const float* x, const float* gamma, const float* beta, void* y_
 
 /* NCHW fp32 tile batch [B,C,1024,1024] (C = 3 or 1) -> bf16 im2col rows [B*4096, C*256] (k = c*256 + ky*16 + kx)
  * for the patch-embed / hfc-embed GEMMs (image_encoder.py:409-417, 442-450) and, if C == 3 and gray != NULL, the
- * bf16 grayscale plane [B,1024,1024] (0.2989 R + 0.587 G + 0.114 B, network.py:41). */
-int wm_patchify(const float* img, void* patches_bf16, void* gray_bf16, int B, int C, void* stream);
+ * bf16 grayscale plane [B,1024,1024] (0.2989 R + 0.587 G + 0.114 B, network.py:41).  gray_split = 1: the plane is
+ * written as rows of 3072 = [hi | lo | hi], hi = bf16(g), lo = bf16(g - hi): the A operand of the SPLIT low-pass GEMM
+ * (weight [Lh | Lh | Ll]), which reproduces the reference's fp32 fft2 / ifft2 (network.py:43-55) to ~2e-6 instead of
+ * the 1e-3 of single bf16 operands (x_hfc is a small difference of O(1) numbers on smooth imagery). */
+int wm_patchify(const float* img, void* patches_bf16, void* gray_bf16, int gray_split, int B, int C, void* stream);
 
 /* Batched 2-D transpose: in [batch, R, C] -> out [batch, C, R]; elt_bytes 2 or 4. */
 int wm_transpose(const void* in, void* out, int batch, int R, int C, int elt_bytes, void* stream);
+
+/* fp32 in [batch, R, C] -> bf16 hi / lo split of its transpose: out[b][c / 2][seg][c % 2][r], seg 0 and 2 = bf16(v),
+ * seg 1 = bf16(v - bf16(v)); R, C multiples of 64.  With in = the first low-pass product [B, 1024 (y), 2048 (x', re/im)]
+ * this is the A operand [B*1024, 6144] of the second split low-pass GEMM (network.py:43-55). */
+int wm_transpose_split(const float* in, void* out_bf16, int batch, int R, int C, void* stream);
 
 /* x_hfc = |gray(img) - lowpass| (network.py:53-55) where low_t [B,1024(x),1024(y)] fp32 is the TRANSPOSED low-pass
  * image from the two DFT-operator GEMMs; writes hfc_embed im2col rows [B*4096, 256] bf16 (image_encoder.py:442-450)

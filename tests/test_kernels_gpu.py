@@ -115,6 +115,38 @@ def test_patchify_and_gray():
     assert (gray.float() - g).abs().max().item() < 0.02
 
 
+def test_patchify_gray_split():
+    """gray_split: rows [hi | lo | hi] with hi = bf16(g) (bit-identical to the unsplit plane), hi + lo = g to ~2^-17."""
+    B = 2
+    img = rnd(B, 3, 1024, 1024, seed=15, dtype=torch.float32)
+    patches = torch.empty(B * 4096, 768, device=DEV, dtype=torch.bfloat16)
+    gray = torch.empty(B, 1024, 1024, device=DEV, dtype=torch.bfloat16)
+    ops.patchify(img, patches, gray)
+    patches2 = torch.empty_like(patches)
+    gs = torch.empty(B * 1024, 3072, device=DEV, dtype=torch.bfloat16)
+    ops.patchify(img, patches2, gs, True)
+    assert torch.equal(patches, patches2)
+    assert torch.equal(gs[:, :1024], gray.view(B * 1024, 1024)) and torch.equal(gs[:, 2048:], gs[:, :1024])
+    g = (0.2989 * img[:, 0] + 0.587 * img[:, 1] + 0.114 * img[:, 2]).view(B * 1024, 1024)
+    err = (gs[:, :1024].float() + gs[:, 1024:2048].float() - g).abs().max().item()
+    assert err <= g.abs().max().item() * 2 ** -15, err
+
+
+def test_transpose_split():
+    """fp32 [b, R, C] -> out[b][c / 2][seg][c % 2][r] with seg (hi, lo, hi): bit-exact against the same split in torch."""
+    b, R, C = 2, 128, 192
+    x = rnd(b, R, C, seed=17, dtype=torch.float32) * 3
+    out = torch.empty(b * (C // 2), 6 * R, device=DEV, dtype=torch.bfloat16)
+    ops.transpose_split(x, out)
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+
+    def lay(t):  # [b, R, C] -> [b, C/2, 2, R]
+        return t.transpose(1, 2).reshape(b, C // 2, 2, R)
+    ref = torch.stack([lay(hi), lay(lo), lay(hi)], dim=2).reshape(b * (C // 2), 6 * R)
+    assert torch.equal(out, ref)
+
+
 @pytest.mark.parametrize("R,C,dt", [(1024, 4096, torch.bfloat16), (4096, 256, torch.float32), (100, 70, torch.float32),
                                      (1024, 2048, torch.bfloat16), (100, 70, torch.bfloat16), (67, 33, torch.bfloat16)])
 def test_transpose(R, C, dt):

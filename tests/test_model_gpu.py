@@ -96,7 +96,7 @@ def test_vit_b_vs_reference_golden(golden_dir):
     # high-pass image vs the reference's FFT path
     h = mask.float().contiguous().view(-1)
     got = h[torch.from_numpy(sample_positions(h.numel(), "x_hfc")).to(DEV)].cpu().numpy()
-    assert np.abs(got - g["x_hfc.samples"]).max() <= 2e-2
+    assert np.abs(got - g["x_hfc.samples"]).max() <= 2e-4  # split low-pass products (single bf16 operands: 6e-3)
     # drop-in PostProcess on the CUDA outputs vs the reference PostProcess on the reference outputs
     res = post["bbox"](out, torch.tensor([[1024, 1024]], device=DEV))
     assert res[0]["labels"].dtype == torch.int64
@@ -105,6 +105,38 @@ def test_vit_b_vs_reference_golden(golden_dir):
     if res[0]["labels"].shape[0] == n_ref:
         assert (res[0]["labels"].cpu().numpy() == g["pp0.labels"]).mean() >= 0.9
         assert np.abs(res[0]["boxes"].cpu().numpy() - g["pp0.boxes"]).max() <= 5e-3 * 1024
+
+
+def test_highpass_on_smooth_imagery():
+    """x_hfc = |gray - lowpass| is a small difference of O(1) numbers on smooth (natural-image-like) tiles; with
+    single bf16 operands in the DFT-operator GEMMs the error (1.4e-3 mean) is 5 % of the signal on a 1/f^1.5 field.  The
+    split (hi + lo) products must reproduce the reference's fp32 FFT path (network.py:43-55) to 1e-3 of the signal."""
+    gen = torch.Generator().manual_seed(5)
+    fy, fx = torch.fft.fftfreq(1024)[:, None], torch.fft.fftfreq(1024)[None, :]
+    f = torch.sqrt(fy ** 2 + fx ** 2)
+    f[0, 0] = 1.0
+    tiles = []
+    for alpha in (1.0, 1.5):
+        spec = torch.complex(torch.randn(1024, 1024, generator=gen), torch.randn(1024, 1024, generator=gen)) / f ** alpha
+        field = torch.fft.ifft2(spec).real
+        field = (field - field.mean()) / field.std()
+        tiles.append(torch.stack([field + 0.3, 0.8 * field - 0.1, 1.1 * field + 0.5]))
+    tiles = torch.stack(tiles).float().contiguous()
+    ref = om.hfc_highpass(tiles)
+    model = build("vit_t", 51)
+    eng = model.image_encoder.engine()
+    assert eng.hfc_precision == "split"
+    with torch.no_grad():
+        _, a_hfc, hfc_img = eng.highpass(tiles.to(DEV), want_image=True)
+    torch.cuda.synchronize()
+    for i, alpha in enumerate((1.0, 1.5)):
+        d = (hfc_img[i].cpu() - ref[i]).abs()
+        rel = d.mean().item() / ref[i].mean().item()
+        print(f"[highpass 1/f^{alpha}] mean |x_hfc| {ref[i].mean():.4f} mean err {d.mean():.2e} max err {d.max():.2e} rel {rel:.2e}")
+        assert rel <= 1e-3 and d.max().item() <= 2e-4
+    # the im2col rows of hfc_embed are the bf16 rounding of the same image
+    rows = torch.nn.functional.unfold(ref, 16, stride=16).transpose(1, 2).reshape(-1, 256)
+    assert (a_hfc.float().cpu() - rows).abs().max().item() <= rows.abs().max().item() * 2 ** -8
 
 
 def test_tiny_model_stage_parity_vs_oracle():
@@ -128,7 +160,7 @@ def test_tiny_model_stage_parity_vs_oracle():
         print(f"[stage {name}] max-abs {d.max():.3e} mean-abs {d.mean():.3e} |ref|max {ref.abs().max():.2f}")
         assert d.max().item() <= tol_max, name
 
-    cmp("x_hfc", hfc_img, otaps["x_hfc"], 2e-2)
+    cmp("x_hfc", hfc_img, otaps["x_hfc"], 2e-4)
     cmp("after_hfc", taps["after_hfc"], otaps["after_hfc"], 6e-2)  # (measured 3.1e-2 ... 3.9e-2 on |x| <= 10)
     cmp("block0", taps["block0"], otaps["block0"], 6e-2)
     cmp("block1", taps["block1"], otaps["block1"], 6e-2)

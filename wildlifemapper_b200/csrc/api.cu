@@ -11,7 +11,8 @@
 namespace wm {
 int layernorm_launch(const float*, const float*, const float*, __nv_bfloat16*, float*, const float*, int,
                      __nv_bfloat16*, int, int, float, cudaStream_t);
-int patchify_launch(const float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
+int patchify_launch(const float*, __nv_bfloat16*, __nv_bfloat16*, int, int, int, cudaStream_t);
+int transpose_split_launch(const float*, __nv_bfloat16*, int, int, int, cudaStream_t);
 int transpose_launch(const void*, void*, int, int, int, int, cudaStream_t);
 int hfc_finalize_launch(const float*, const float*, __nv_bfloat16*, float*, int, cudaStream_t);
 int add_cast_launch(const float*, const float*, int, __nv_bfloat16*, int, int, cudaStream_t);
@@ -263,12 +264,13 @@ int wm_layernorm(const float* x, const float* gamma, const float* beta, void* y_
                       "wm_layernorm");
 }
 
-int wm_patchify(const float* img, void* patches_bf16, void* gray_bf16, int B, int C, void* stream) {
+int wm_patchify(const float* img, void* patches_bf16, void* gray_bf16, int gray_split, int B, int C, void* stream) {
   if (int rc = ensure_device()) return rc;
   if (B <= 0 || B > 65535 || (C != 1 && C != 3)) return fail(WM_ERR_SHAPE, "wm_patchify: B=%d C=%d", B, C);
+  if (gray_split != 0 && gray_split != 1) return fail(WM_ERR_SHAPE, "wm_patchify: gray_split must be 0 or 1");
   if (!aligned16(img) || !aligned16(patches_bf16) || !aligned16(gray_bf16)) return fail(WM_ERR_ALIGN, "wm_patchify: alignment");
   return check_launch(wm::patchify_launch(img, reinterpret_cast<__nv_bfloat16*>(patches_bf16),
-                                          reinterpret_cast<__nv_bfloat16*>(gray_bf16), B, C, (cudaStream_t)stream),
+                                          reinterpret_cast<__nv_bfloat16*>(gray_bf16), gray_split, B, C, (cudaStream_t)stream),
                       "wm_patchify");
 }
 
@@ -276,6 +278,15 @@ int wm_transpose(const void* in, void* out, int batch, int R, int C, int elt_byt
   if (int rc = ensure_device()) return rc;
   if (batch <= 0 || R <= 0 || C <= 0 || batch > 65535) return fail(WM_ERR_SHAPE, "wm_transpose: bad shape");
   return check_launch(wm::transpose_launch(in, out, batch, R, C, elt_bytes, (cudaStream_t)stream), "wm_transpose");
+}
+
+int wm_transpose_split(const float* in, void* out_bf16, int batch, int R, int C, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (batch <= 0 || batch > 65535 || R <= 0 || C <= 0 || R % 64 != 0 || C % 64 != 0)
+    return fail(WM_ERR_SHAPE, "wm_transpose_split: batch=%d R=%d C=%d (R and C must be multiples of 64)", batch, R, C);
+  if (!aligned16(in) || !aligned16(out_bf16)) return fail(WM_ERR_ALIGN, "wm_transpose_split: alignment");
+  return check_launch(wm::transpose_split_launch(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), batch, R, C, (cudaStream_t)stream),
+                      "wm_transpose_split");
 }
 
 int wm_hfc_finalize(const float* img, const float* low_t, void* patches_bf16, float* hfc_img, int B, void* stream) {

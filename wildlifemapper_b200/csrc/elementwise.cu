@@ -85,7 +85,10 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, __nv
 
 // ------------------------------------------------------------------ patchify (+ grayscale)
 // One block per (image, patch row py): reads C x 16 x 1024 fp32 (coalesced rows), writes 64 patches x C*256 bf16.
-template <int C>
+// The grayscale plane feeds the low-pass DFT-operator GEMMs.  SPLIT: rows of 3072 = [hi | lo | hi] with hi = bf16(g),
+// lo = bf16(g - hi): against the weight [Lh | Lh | Ll] one GEMM accumulates g_hi Lh + g_lo Lh + g_hi Ll in fp32, i.e. the
+// product to ~2^-17 instead of 2^-9 (x_hfc = |g - low| is a small difference of O(1) numbers on smooth imagery).
+template <int C, bool SPLIT>
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ patches,
                                                        __nv_bfloat16* __restrict__ gray) {
   const int b = blockIdx.y, py = blockIdx.x;
@@ -108,17 +111,28 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
       g.y = 0.2989f * c[0].y + 0.587f * c[C > 1 ? 1 : 0].y + 0.114f * c[C > 2 ? 2 : 0].y;
       g.z = 0.2989f * c[0].z + 0.587f * c[C > 1 ? 1 : 0].z + 0.114f * c[C > 2 ? 2 : 0].z;
       g.w = 0.2989f * c[0].w + 0.587f * c[C > 1 ? 1 : 0].w + 0.114f * c[C > 2 ? 2 : 0].w;
-      *reinterpret_cast<uint2*>(gray + ((size_t)b * 1024 + py * 16 + ky) * 1024 + x4 * 4) =
-          make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
+      const uint2 hi = make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
+      if (!SPLIT) {
+        *reinterpret_cast<uint2*>(gray + ((size_t)b * 1024 + py * 16 + ky) * 1024 + x4 * 4) = hi;
+      } else {
+        const uint2 lo = make_uint2(pack_bf16(g.x - __uint_as_float(hi.x << 16), g.y - __uint_as_float(hi.x & 0xffff0000u)),
+                                    pack_bf16(g.z - __uint_as_float(hi.y << 16), g.w - __uint_as_float(hi.y & 0xffff0000u)));
+        __nv_bfloat16* grow = gray + ((size_t)b * 1024 + py * 16 + ky) * 3072 + x4 * 4;
+        *reinterpret_cast<uint2*>(grow) = hi;
+        *reinterpret_cast<uint2*>(grow + 1024) = lo;
+        *reinterpret_cast<uint2*>(grow + 2048) = hi;
+      }
     }
   }
 }
 
-int patchify_launch(const float* img, __nv_bfloat16* patches, __nv_bfloat16* gray, int B, int C, cudaStream_t st) {
-  if (C == 3)
-    patchify_kernel<3><<<dim3(64, B), 256, 0, st>>>(img, patches, gray);
+int patchify_launch(const float* img, __nv_bfloat16* patches, __nv_bfloat16* gray, int gray_split, int B, int C, cudaStream_t st) {
+  if (C == 3 && gray_split)
+    patchify_kernel<3, true><<<dim3(64, B), 256, 0, st>>>(img, patches, gray);
+  else if (C == 3)
+    patchify_kernel<3, false><<<dim3(64, B), 256, 0, st>>>(img, patches, gray);
   else if (C == 1)
-    patchify_kernel<1><<<dim3(64, B), 256, 0, st>>>(img, patches, nullptr);
+    patchify_kernel<1, false><<<dim3(64, B), 256, 0, st>>>(img, patches, nullptr);
   else
     return WM_ERR_SHAPE;
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
@@ -182,6 +196,41 @@ int transpose_launch(const void* in, void* out, int batch, int R, int C, int elt
     transpose_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)in, (uint32_t*)out, R, C);
   else
     return WM_ERR_SHAPE;
+  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+}
+
+// fp32 [batch, R, C] -> bf16 hi / lo split of the transpose, laid out as the A operand of the second low-pass GEMM:
+// out[b][c / 2][seg][c % 2][r], seg 0 and 2 = hi = bf16(v), seg 1 = lo = bf16(v - hi)  (rows of 6 R elements, matching the
+// weight [W2h | W2h | W2l]).  64 x 64 tiles; every warp store is 128 contiguous bytes (64 r values of one column).
+__global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C) {
+  __shared__ float tile[64][65];
+  const size_t boff = (size_t)blockIdx.z * R * C;
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty + 8 * i;
+    const float2 v = *reinterpret_cast<const float2*>(in + boff + (size_t)r * C + c0 + 2 * tx);
+    tile[ty + 8 * i][2 * tx] = v.x;
+    tile[ty + 8 * i][2 * tx + 1] = v.y;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + ty + 8 * i;
+    const float a = tile[2 * tx][ty + 8 * i], b = tile[2 * tx + 1][ty + 8 * i];
+    const uint32_t hi = pack_bf16(a, b);
+    const uint32_t lo = pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + ((size_t)blockIdx.z * (C / 2) + (c >> 1)) * (size_t)(6 * R) + (size_t)(c & 1) * R + r0) + tx;
+    o[0] = hi;
+    o[R] = lo;       // + 2 R elements = R words
+    o[2 * R] = hi;
+  }
+}
+
+int transpose_split_launch(const float* in, __nv_bfloat16* out, int batch, int R, int C, cudaStream_t st) {
+  if (R % 64 != 0 || C % 64 != 0) return WM_ERR_SHAPE;
+  transpose_split_kernel<<<dim3(C / 64, R / 64, batch), 256, 0, st>>>(in, out, R, C);
   return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
 }
 

@@ -18,6 +18,7 @@ Data layout in HBM (M = B*4096 token rows, row = image-major, then y, then x):
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -90,6 +91,12 @@ class EncoderEngine:
         # modules hang on API-visible tensors, see modeling/common.py::attach_twin): im2col rows / encoder features
         self.gen_rows = 0
         self.gen_feat = 0
+        # low-pass products of MedSAM.fft: "split" = hi + lo bf16 terms of the image, the DFT operator and the intermediate
+        # (3 tensor-core products per stage, ~2e-6 absolute, i.e. the reference's fp32 FFT); "bf16" = single bf16 operands
+        # (1e-3 absolute: fine on noise-like tiles, 5 % of x_hfc on smooth 1/f^1.5 imagery).  WM_HFC_PRECISION overrides.
+        self.hfc_precision = os.environ.get("WM_HFC_PRECISION", "split")
+        if self.hfc_precision not in ("split", "bf16"):
+            raise ValueError(f"WM_HFC_PRECISION must be 'split' or 'bf16', got {self.hfc_precision!r}")
 
     # ------------------------------------------------------------------ weight preparation
     def prepare(self, sd: Dict[str, torch.Tensor]) -> None:
@@ -120,8 +127,14 @@ class EncoderEngine:
         w["back_b"] = _f32(g(a + "proj_back.bias"))
         # low-pass DFT operator (constant): GEMM1 weight rows interleaved (x', part), GEMM2 weight [y', (part, y)]
         Lr, Li = lowpass_operator_tables()
-        w["lp1"] = _bf(torch.stack([Lr, Li], dim=1).reshape(2048, 1024).to(dev))
-        w["lp2"] = _bf(torch.cat([Lr, -Li], dim=1).to(dev))
+        lp1 = torch.stack([Lr, Li], dim=1).reshape(2048, 1024).to(dev)
+        lp2 = torch.cat([Lr, -Li], dim=1).to(dev)
+        w["lp1"], w["lp2"] = _bf(lp1), _bf(lp2)
+        if self.hfc_precision == "split":  # [Wh | Wh | Wl] against the operand rows [hi | lo | hi]
+            for n, full in (("lp1", lp1), ("lp2", lp2)):
+                hi = w[n]
+                lo = _bf(full - hi.to(torch.float64))
+                w[n + "s"] = torch.cat([hi, hi, lo], dim=1).contiguous()
         for i in range(self.depth):
             b = f"blocks.{i}."
             p = f"b{i}."
@@ -157,14 +170,23 @@ class EncoderEngine:
         ws, w = self.ws, self.w
         self.gen_rows += 1
         a_patch = ws.get("a_patch", (B * NTOK, 768), torch.bfloat16)
-        gray = ws.get("gray", (B * 1024, 1024), torch.bfloat16)
-        ops.patchify(img, a_patch, gray)
-        p1 = ws.get("lp_p1", (B * 1024, 2048), torch.bfloat16)
-        _gemm(gray, w["lp1"], out_bf16=p1)
-        p1t = ws.get("lp_p1t", (B, 2048, 1024), torch.bfloat16)
-        ops.transpose(p1.view(B, 1024, 2048), p1t)
         low_t = ws.get("lp_low", (B * 1024, 1024), torch.float32)
-        _gemm(p1t.view(B * 1024, 2048), w["lp2"], out_f32=low_t)
+        if self.hfc_precision == "split":
+            gray = ws.get("gray", (B * 1024, 3072), torch.bfloat16)
+            ops.patchify(img, a_patch, gray, True)
+            p1 = ws.get("lp_p1", (B * 1024, 2048), torch.float32)
+            _gemm(gray, w["lp1s"], out_f32=p1)
+            p1t = ws.get("lp_p1t", (B * 1024, 6144), torch.bfloat16)
+            ops.transpose_split(p1.view(B, 1024, 2048), p1t)
+            _gemm(p1t, w["lp2s"], out_f32=low_t)
+        else:
+            gray = ws.get("gray", (B * 1024, 1024), torch.bfloat16)
+            ops.patchify(img, a_patch, gray)
+            p1 = ws.get("lp_p1", (B * 1024, 2048), torch.bfloat16)
+            _gemm(gray, w["lp1"], out_bf16=p1)
+            p1t = ws.get("lp_p1t", (B, 2048, 1024), torch.bfloat16)
+            ops.transpose(p1.view(B, 1024, 2048), p1t)
+            _gemm(p1t.view(B * 1024, 2048), w["lp2"], out_f32=low_t)
         a_hfc = ws.get("a_hfc", (B * NTOK, 256), torch.bfloat16)
         hfc_img = torch.empty(B, 1, 1024, 1024, device=img.device, dtype=torch.float32) if want_image else None
         ops.hfc_finalize(img, low_t, a_hfc, hfc_img)

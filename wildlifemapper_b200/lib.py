@@ -28,7 +28,8 @@ SIGNATURES = {
     "wm_num_sms": [],
     "wm_conv3x3_nhwc_bf16": [_p, _p, _p, _p, _i, _i, _i, _p],
     "wm_layernorm": [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _f, _p],
-    "wm_patchify": [_p, _p, _p, _i, _i, _p],
+    "wm_patchify": [_p, _p, _p, _i, _i, _i, _p],
+    "wm_transpose_split": [_p, _p, _i, _i, _i, _p],
     "wm_transpose": [_p, _p, _i, _i, _i, _i, _p],
     "wm_hfc_finalize": [_p, _p, _p, _p, _i, _p],
     "wm_add_cast": [_p, _p, _i, _p, _i, _i, _p],

@@ -109,17 +109,17 @@ _define("layernorm(Tensor x, Tensor gamma, Tensor beta, Tensor(a!)? y_bf16, Tens
         "int add_mod, Tensor(c!)? y2_bf16, float eps) -> ()", _layernorm)
 
 
-def _patchify(img, patches, gray):
+def _patchify(img, patches, gray, gray_split=False):
     _chk(img, torch.float32, "patchify.img"); _chk(patches, torch.bfloat16, "patchify.patches")
     _chk(gray, torch.bfloat16, "patchify.gray")
     assert img.is_contiguous() and img.dim() == 4 and tuple(img.shape[2:]) == (1024, 1024), img.shape
     B, Cc = img.shape[0], img.shape[1]
     assert patches.is_contiguous() and patches.numel() == B * 4096 * 256 * Cc
-    assert gray is None or (Cc == 3 and gray.is_contiguous() and gray.numel() == B * 1024 * 1024)
-    _lib.call("wm_patchify", img.data_ptr(), patches.data_ptr(), _ptr(gray), B, Cc, _stream())
+    assert gray is None or (Cc == 3 and gray.is_contiguous() and gray.numel() == B * 1024 * 1024 * (3 if gray_split else 1))
+    _lib.call("wm_patchify", img.data_ptr(), patches.data_ptr(), _ptr(gray), int(bool(gray_split)), B, Cc, _stream())
 
 
-_define("patchify(Tensor img, Tensor(a!) patches, Tensor(b!)? gray) -> ()", _patchify)
+_define("patchify(Tensor img, Tensor(a!) patches, Tensor(b!)? gray, bool gray_split=False) -> ()", _patchify)
 
 
 def _transpose(x, out):
@@ -130,6 +130,17 @@ def _transpose(x, out):
 
 
 _define("transpose(Tensor x, Tensor(a!) out) -> ()", _transpose)
+
+
+def _transpose_split(x, out):
+    _chk(x, torch.float32, "transpose_split.x"); _chk(out, torch.bfloat16, "transpose_split.out")
+    assert x.is_contiguous() and out.is_contiguous() and x.dim() == 3
+    b, R, Cc = x.shape
+    assert out.numel() == 3 * x.numel()
+    _lib.call("wm_transpose_split", x.data_ptr(), out.data_ptr(), b, R, Cc, _stream())
+
+
+_define("transpose_split(Tensor x, Tensor(a!) out) -> ()", _transpose_split)
 
 
 def _hfc_finalize(img, low_t, patches, hfc_img):

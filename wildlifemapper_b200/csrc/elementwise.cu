@@ -288,186 +288,12 @@ int add_cast_launch(const float* a, const float* b, int b_mod, __nv_bfloat16* ou
 }
 
 // ------------------------------------------------------------------ decoder attention (small head dims)
-// One THREAD per query row: q and the output accumulator live in registers, key/value tiles of 128 keys are staged
-// in smem as fp32 and read by broadcast (all threads of a warp read the same key), online softmax in the exp2
-// domain over chunks of 8 keys.  SPLIT = 4 partitions every key tile across 4 thread groups (for few queries,
-// e.g. 51 tokens -> image) and merges the partial (m, l, acc) through smem.
-//
-// KSPLIT > 1 (few queries against many keys: 51 tokens -> 4096 image positions is a 256-CTA launch otherwise, 1.7 CTAs per
-// SM each walking 32 key tiles): a thread-block CLUSTER of KSPLIT CTAs shares the queries of one block, CTA `rank` takes
-// the key tiles rank, rank + KSPLIT, ...; the partial softmax states are merged by rank 0 through distributed shared
-// memory (flash-decoding inside a cluster: no second kernel, no global scratch).
+// (Round 1 ran one THREAD per query row on the CUDA cores, 253 us for 51 queries x 4096 keys at batch 32; superseded by the
+// warp-level tensor-core kernel below and removed from the build.)
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
   float v;
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
   return v;
-}
-
-template <int HD, int SPLIT, int KSPLIT>
-__global__ void __launch_bounds__(256) attn_small_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
-                                                         const __nv_bfloat16* __restrict__ k, int ldk,
-                                                         const __nv_bfloat16* __restrict__ v, int ldv,
-                                                         __nv_bfloat16* __restrict__ out, int ldo, int Tq, int Tk,
-                                                         float scale_log2e) {
-  constexpr int QB = 256 / SPLIT;    // queries per block
-  constexpr int KCH = 128 / SPLIT;   // keys of each tile handled by one group
-  __shared__ __align__(16) float sK[128][HD];
-  __shared__ __align__(16) float sV[128][HD];
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int grp = threadIdx.x / QB, ql = threadIdx.x % QB;
-  const int krank = KSPLIT > 1 ? (int)(blockIdx.x % KSPLIT) : 0;  // (cluster dims (KSPLIT,1,1): rank == blockIdx.x % KSPLIT)
-  const int qi = (int)(blockIdx.x / KSPLIT) * QB + ql;
-  const bool q_ok = qi < Tq;
-  float qr[HD], acc[HD];
-#pragma unroll
-  for (int d = 0; d < HD; ++d) { qr[d] = 0.f; acc[d] = 0.f; }
-  if (q_ok) {
-    const uint4* qp = reinterpret_cast<const uint4*>(q + (size_t)(b * Tq + qi) * ldq + h * HD);
-#pragma unroll
-    for (int d8 = 0; d8 < HD / 8; ++d8) {
-      const uint4 u = __ldg(qp + d8);
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(h2[e]);
-        qr[d8 * 8 + 2 * e] = f.x * scale_log2e;
-        qr[d8 * 8 + 2 * e + 1] = f.y * scale_log2e;
-      }
-    }
-  }
-  float m_run = -INFINITY, l_run = 0.f;
-  for (int k0 = krank * 128; k0 < Tk; k0 += 128 * KSPLIT) {
-    __syncthreads();
-    // stage 128 keys x HD of K and V (16-byte global loads, zero fill past Tk)
-    for (int i = threadIdx.x; i < 128 * (HD / 8); i += 256) {
-      const int kk = i / (HD / 8), d8 = i % (HD / 8);
-      uint4 uk = make_uint4(0, 0, 0, 0), uv = make_uint4(0, 0, 0, 0);
-      if (k0 + kk < Tk) {
-        uk = __ldg(reinterpret_cast<const uint4*>(k + (size_t)(b * Tk + k0 + kk) * ldk + h * HD) + d8);
-        uv = __ldg(reinterpret_cast<const uint4*>(v + (size_t)(b * Tk + k0 + kk) * ldv + h * HD) + d8);
-      }
-      const __nv_bfloat162* hk = reinterpret_cast<const __nv_bfloat162*>(&uk);
-      const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&uv);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 fk = __bfloat1622float2(hk[e]), fv = __bfloat1622float2(hv[e]);
-        sK[kk][d8 * 8 + 2 * e] = fk.x; sK[kk][d8 * 8 + 2 * e + 1] = fk.y;
-        sV[kk][d8 * 8 + 2 * e] = fv.x; sV[kk][d8 * 8 + 2 * e + 1] = fv.y;
-      }
-    }
-    __syncthreads();
-    const int kbeg = grp * KCH;
-    const int kend = min(kbeg + KCH, Tk - k0);  // may be <= kbeg
-    for (int c0 = kbeg; c0 < kend; c0 += 8) {
-      float sc[8];
-      float mx = m_run;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        float a = 0.f;
-        const float4* kr = reinterpret_cast<const float4*>(&sK[c0 + u][0]);  // c0+u < 128 always
-#pragma unroll
-        for (int d4 = 0; d4 < HD / 4; ++d4) {
-          const float4 kv4 = kr[d4];
-          a = fmaf(qr[4 * d4], kv4.x, a); a = fmaf(qr[4 * d4 + 1], kv4.y, a);
-          a = fmaf(qr[4 * d4 + 2], kv4.z, a); a = fmaf(qr[4 * d4 + 3], kv4.w, a);
-        }
-        sc[u] = (c0 + u < kend) ? a : -INFINITY;
-        mx = fmaxf(mx, sc[u]);
-      }
-      const float alpha = ex2_approx(m_run - mx);  // 0 on the first chunk
-      m_run = mx;
-      l_run *= alpha;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] *= alpha;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float pe = ex2_approx(sc[u] - mx);  // 0 for masked keys
-        l_run += pe;
-        const float4* vr = reinterpret_cast<const float4*>(&sV[c0 + u][0]);
-#pragma unroll
-        for (int d4 = 0; d4 < HD / 4; ++d4) {
-          const float4 vv = vr[d4];
-          acc[4 * d4] = fmaf(pe, vv.x, acc[4 * d4]); acc[4 * d4 + 1] = fmaf(pe, vv.y, acc[4 * d4 + 1]);
-          acc[4 * d4 + 2] = fmaf(pe, vv.z, acc[4 * d4 + 2]); acc[4 * d4 + 3] = fmaf(pe, vv.w, acc[4 * d4 + 3]);
-        }
-      }
-    }
-  }
-  if (SPLIT > 1) {
-    // merge the SPLIT partial softmax states of each query through smem (reuse the K/V staging buffers)
-    __syncthreads();
-    float* sm = &sK[0][0];               // [SPLIT][QB] m
-    float* sl = sm + 256;                // [SPLIT][QB] l
-    float* sa = &sV[0][0];               // [SPLIT][QB][HD] acc  (256*HD floats <= 128*HD*... guarded below)
-    static_assert(SPLIT == 1 || 256 * HD <= 128 * HD * 2, "merge scratch");
-    sm[grp * QB + ql] = m_run;
-    sl[grp * QB + ql] = l_run;
-    __syncthreads();
-    float m_all = -INFINITY;
-#pragma unroll
-    for (int g = 0; g < SPLIT; ++g) m_all = fmaxf(m_all, sm[g * QB + ql]);
-    const float w = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_all);
-    // two rounds: acc of groups {0,1} then {2,3} would not fit at once for HD=32; accumulate via atomics-free tree
-    for (int g = 0; g < SPLIT; ++g) {
-      __syncthreads();
-      if (grp == g) {
-#pragma unroll
-        for (int d = 0; d < HD; ++d) {
-          float* cell = sa + (size_t)ql * HD + d;
-          *cell = (g == 0 ? 0.f : *cell) + acc[d] * w;
-        }
-        float* lc = sl + SPLIT * QB + ql;  // merged l
-        *lc = (g == 0 ? 0.f : *lc) + l_run * w;
-      }
-    }
-    __syncthreads();
-    if (KSPLIT > 1) {
-      // cross-CTA merge: every CTA publishes (m_all, merged l, merged acc) of its key subset, rank 0 combines them
-      float* smx = sl + (SPLIT + 1) * QB;  // [QB] m_all of this CTA
-      if (grp == 0) smx[ql] = m_all;
-      cluster_sync();
-      if (krank == 0 && grp == 0) {
-        float mg = -INFINITY;
-#pragma unroll
-        for (int rk = 0; rk < KSPLIT; ++rk) mg = fmaxf(mg, ld_dsmem_f32(mapa_shared(smem_u32(smx + ql), rk)));
-        float lg = 0.f, og[HD];
-#pragma unroll
-        for (int d = 0; d < HD; ++d) og[d] = 0.f;
-#pragma unroll 1
-        for (int rk = 0; rk < KSPLIT; ++rk) {
-          const float mr = ld_dsmem_f32(mapa_shared(smem_u32(smx + ql), rk));
-          const float wr = (mr == -INFINITY) ? 0.f : ex2_approx(mr - mg);
-          lg = fmaf(ld_dsmem_f32(mapa_shared(smem_u32(sl + SPLIT * QB + ql), rk)), wr, lg);
-          const uint32_t ar = mapa_shared(smem_u32(sa + (size_t)ql * HD), rk);
-#pragma unroll
-          for (int d = 0; d < HD; ++d) og[d] = fmaf(ld_dsmem_f32(ar + 4 * d), wr, og[d]);
-        }
-        if (q_ok) {
-          const float inv = 1.0f / lg;
-          __nv_bfloat16* op = out + (size_t)(b * Tq + qi) * ldo + h * HD;
-#pragma unroll
-          for (int d = 0; d < HD; d += 2) *reinterpret_cast<uint32_t*>(op + d) = pack_bf16(og[d] * inv, og[d + 1] * inv);
-        }
-      }
-      cluster_sync();  // the peers' shared memory must stay alive until rank 0 has read it
-      return;
-    }
-    if (grp == 0 && q_ok) {
-      const float inv = 1.0f / sl[SPLIT * QB + ql];
-      __nv_bfloat16* op = out + (size_t)(b * Tq + qi) * ldo + h * HD;
-#pragma unroll
-      for (int d = 0; d < HD; d += 2)
-        *reinterpret_cast<uint32_t*>(op + d) = pack_bf16(sa[(size_t)ql * HD + d] * inv, sa[(size_t)ql * HD + d + 1] * inv);
-    }
-  } else if (q_ok) {
-    const float inv = 1.0f / l_run;
-    __nv_bfloat16* op = out + (size_t)(b * Tq + qi) * ldo + h * HD;
-#pragma unroll
-    for (int d8 = 0; d8 < HD / 8; ++d8)
-      reinterpret_cast<uint4*>(op)[d8] =
-          make_uint4(pack_bf16(acc[8 * d8] * inv, acc[8 * d8 + 1] * inv), pack_bf16(acc[8 * d8 + 2] * inv, acc[8 * d8 + 3] * inv),
-                     pack_bf16(acc[8 * d8 + 4] * inv, acc[8 * d8 + 5] * inv), pack_bf16(acc[8 * d8 + 6] * inv, acc[8 * d8 + 7] * inv));
-  }
 }
 
 // ------------------------------------------------------------------ decoder attention on warp-level tensor-core MMAs
@@ -704,36 +530,7 @@ int attn_small_launch(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, i
                              : attn_mma_launch<32, 1>(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Tq, Tk, sl2, st);
     return WM_ERR_SHAPE;
   }
-  const bool split = Tq <= 1024;
-  // few queries, many keys (tokens -> image): split the keys over a cluster of 8 CTAs
-  const bool ksplit = split && Tk >= 2048;
-  if (ksplit) {
-    constexpr int KS = 8;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(((Tq + 63) / 64) * KS, H, B);
-    cfg.blockDim = dim3(256, 1, 1);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = KS;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e;
-    if (hd == 16) e = cudaLaunchKernelEx(&cfg, attn_small_kernel<16, 4, KS>, q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, sl2);
-    else if (hd == 32) e = cudaLaunchKernelEx(&cfg, attn_small_kernel<32, 4, KS>, q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, sl2);
-    else return WM_ERR_SHAPE;
-    return e == cudaSuccess ? WM_OK : WM_ERR_CUDA;
-  }
-  dim3 grid((Tq + (split ? 63 : 255)) / (split ? 64 : 256), H, B);
-#define WM_AS(HD_, SP_) attn_small_kernel<HD_, SP_, 1><<<grid, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, sl2)
-  if (hd == 16) { if (split) WM_AS(16, 4); else WM_AS(16, 1); }
-  else if (hd == 32) { if (split) WM_AS(32, 4); else WM_AS(32, 1); }
-  else return WM_ERR_SHAPE;
-#undef WM_AS
-  return cudaGetLastError() == cudaSuccess ? WM_OK : WM_ERR_CUDA;
+  return WM_ERR_SHAPE;  // more than 65535 query blocks per (image, head)
 }
 
 }  // namespace wm

@@ -520,7 +520,10 @@ def run_b200(args):
                        "batch_per_gpu": B, "parallelism": f"tile-sharded x{world}, {head['gather']}",
                        "l2": "inputs and activations per step exceed L2 (no flush needed)", "launch": head["launch"],
                        "nms": "score threshold lowered from the reference's 0.5 to 0.05 so that every PostProcess row of the "
-                              "random-init model is an NMS candidate (non-empty NMS work); IoU 0.4, class-agnostic"},
+                              "random-init model is an NMS candidate (non-empty NMS work); IoU 0.4, class-agnostic",
+                       "hfc_precision": os.environ.get("WM_HFC_PRECISION", "split") +
+                                        " (MedSAM.fft low-pass on hi + lo bf16 operands: 3x the DFT-operator GEMM work, the "
+                                        "reference's fp32 FFT to 1e-5; 'bf16' = round-1 single operands)"},
             "eager": head["eager"], "e2e": head.get("e2e"), "gpu_launches": head["gpu_launches"], "clocks": head.get("clocks"),
             "roofline": head["roofline"], "cpu_baseline": cpu, "nms": head["nms"],
             "model_tflops": head.get("model_tflops"), "model_frac_of_bf16_peak": head.get("model_frac_of_bf16_peak"),

@@ -23,7 +23,7 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-from .profiler import ops
+from .profiler import credit, ops
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 GRID = 64
@@ -175,10 +175,11 @@ class EncoderEngine:
             gray = ws.get("gray", (B * 1024, 3072), torch.bfloat16)
             ops.patchify(img, a_patch, gray, True)
             p1 = ws.get("lp_p1", (B * 1024, 2048), torch.float32)
-            _gemm(gray, w["lp1s"], out_f32=p1)
             p1t = ws.get("lp_p1t", (B * 1024, 6144), torch.bfloat16)
-            ops.transpose_split(p1.view(B, 1024, 2048), p1t)
-            _gemm(p1t, w["lp2s"], out_f32=low_t)
+            with credit(1.0 / 3.0):  # three executed products per algorithmic one
+                _gemm(gray, w["lp1s"], out_f32=p1)
+                ops.transpose_split(p1.view(B, 1024, 2048), p1t)
+                _gemm(p1t, w["lp2s"], out_f32=low_t)
         else:
             gray = ws.get("gray", (B * 1024, 1024), torch.bfloat16)
             ops.patchify(img, a_patch, gray)

@@ -12,6 +12,26 @@ import torch
 from .ops import ops as _raw_ops
 
 _ACTIVE: Optional["KernelTimer"] = None
+_CREDIT = 1.0  # fraction of a launch's executed work that is ALGORITHMIC (see credit())
+
+
+class credit:
+    """Context manager: launches inside it are credited `fraction` of their executed FLOPs / bytes.  Used where the engine
+    executes more than the algorithm asks for (the hi + lo split products of the low-pass GEMMs: 3 products per stage for
+    one algorithmic product), so that roofline fractions are not inflated by it."""
+
+    def __init__(self, fraction: float):
+        self.fraction = float(fraction)
+
+    def __enter__(self):
+        global _CREDIT
+        self.prev, _CREDIT = _CREDIT, self.fraction
+        return self
+
+    def __exit__(self, *exc):
+        global _CREDIT
+        _CREDIT = self.prev
+        return False
 
 
 def _nbytes(*ts) -> int:
@@ -82,7 +102,7 @@ class _TimedOps:
             op(*args)
             e.record()
             kind, amount = _work(name, args)
-            t.records.append((name, s, e, kind, amount))
+            t.records.append((name, s, e, kind, amount * _CREDIT))
 
         setattr(self, name, call)  # cache the wrapper
         return call

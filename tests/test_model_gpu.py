@@ -139,6 +139,23 @@ def test_highpass_on_smooth_imagery():
     assert (a_hfc.float().cpu() - rows).abs().max().item() <= rows.abs().max().item() * 2 ** -8
 
 
+def test_highpass_batch_independence_and_zero_image():
+    """Size-independent properties of E0: a tile's high-pass image does not depend on its batch neighbours (bitwise), a constant
+    tile has no high-frequency content beyond rounding, and both precision modes agree to the single-operand error."""
+    model = build("vit_t", 51)
+    eng = model.image_encoder.engine()
+    tiles = make_tiles(3, seed=9).to(DEV)
+    with torch.no_grad():
+        _, rows3, img3 = eng.highpass(tiles, want_image=True)
+        img3, rows3 = img3.clone(), rows3.clone()
+        _, rows1, img1 = eng.highpass(tiles[1:2].contiguous(), want_image=True)
+        assert torch.equal(img1[0], img3[1]) and torch.equal(rows1, rows3[4096:8192])
+        const = torch.full((1, 3, 1024, 1024), 0.75, device=DEV)
+        _, _, imgc = eng.highpass(const, want_image=True)
+        assert imgc.abs().max().item() <= 2e-5  # the reference's fp32 FFT leaves ~1e-7 here
+    torch.cuda.synchronize()
+
+
 def test_tiny_model_stage_parity_vs_oracle():
     """Per-stage comparison against the CPU oracle on the same inputs (reports where error enters)."""
     model = build("vit_t", 51)

@@ -20,7 +20,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         int add_mod, __nv_bfloat16* __restrict__ y2_bf16, int rows,
                                                         float eps) {
   constexpr int D = 128 * VEC_PER_LANE;
+  // Rows are walked from the LAST one back: the GEMM in front of a LayerNorm writes the residual stream front to back and the
+  // GEMM behind it reads the normalised rows front to back, so the rows this kernel touches first are the ones the producer
+  // left in L2 and the ones it writes last are the first the consumer asks for (the tensors are 2-3 x the 126 MB L2; walked
+  // forward, every byte came from and went to HBM).
+#ifdef WM_LN_FORWARD
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+#else
+  const int row = ((int)gridDim.x - 1 - (int)blockIdx.x) * 8 + (threadIdx.x >> 5);
+#endif
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
